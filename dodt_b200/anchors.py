@@ -1,0 +1,99 @@
+"""Host-side (NumPy) anchor geometry that sits between the stages of the front end. These produce
+the INPUTS of the GPU stages (anchor grid for S2, normalised boxes for S3/S5); they mirror the
+reference helpers so that synthetic benchmarks and tests feed the kernels exactly what DODT does.
+They are small per-frame array maths, not part of the accelerated path (SURVEY §8(f) rank 1 lists
+moving them onto the device as the next widening step).
+
+  tile_anchors_3d         avod/core/anchor_generators/grid_anchor_3d_generator.py:39-108
+  box_3d_to_anchor        avod/core/box_3d_encoder.py:85-132
+  project_to_bev          avod/core/anchor_projector.py:13-69
+  project_to_image_space  avod/core/anchor_projector.py:72-156 (+ wavedata calib_utils.py:394-410)
+  offset_to_anchor        avod/core/anchor_encoder.py:99-150
+  reorder_projected_boxes avod/core/anchor_projector.py:254-273
+"""
+import numpy as np
+
+# KITTI Car clusters of avod/configs/pyramid_cars_with_aug_dt_5_tracking.config (2 clusters)
+CAR_ANCHOR_SIZES = [[3.514, 1.581, 1.511], [4.236, 1.653, 1.547]]
+# P2 of avod/tests/datasets/Kitti/tracking/training/calib/0000.txt (public KITTI calibration)
+KITTI_P2 = np.array([[721.5377, 0.0, 609.5593, 44.85728],
+                     [0.0, 721.5377, 172.854, 0.2163791],
+                     [0.0, 0.0, 1.0, 0.002745884]])
+
+
+def tile_anchors_3d(area_extents, anchor_3d_sizes, anchor_stride, ground_plane):
+    """Grid of box_3d anchors N x [x, y, z, l, w, h, ry]: z rows (far to near) x x columns x sizes
+    x two rotations (0, pi/2), placed on the ground plane."""
+    sizes = np.asarray(anchor_3d_sizes)
+    rotations = np.asarray([0, np.pi / 2.0])
+    xs = np.array(np.arange(area_extents[0][0] + anchor_stride[0] / 2.0, area_extents[0][1],
+                            step=anchor_stride[0]), dtype=np.float32)
+    zs = np.array(np.arange(area_extents[2][1] - anchor_stride[1] / 2.0, area_extents[2][0],
+                            step=-anchor_stride[1]), dtype=np.float32)
+    grid = np.stack(np.meshgrid(xs, zs, np.arange(len(sizes)), np.arange(len(rotations))),
+                    axis=4).reshape(-1, 4)
+    a, b, c, d = ground_plane
+    x, z = grid[:, 0], grid[:, 1]
+    y = -(a * x + c * z + d) / b
+    out = np.zeros((len(grid), 7))
+    out[:, 0:3] = np.stack((x, y, z), axis=1)
+    out[:, 3:6] = sizes[np.asarray(grid[:, 2], np.int32)]
+    out[:, 6] = rotations[np.asarray(grid[:, 3], np.int32)]
+    return out
+
+
+def box_3d_to_anchor(boxes_3d):
+    """[x, y, z, l, w, h, ry] -> [x, y, z, dim_x, dim_y, dim_z] by projecting l, w on the axes."""
+    b = np.asarray(boxes_3d).reshape(-1, 7)
+    out = np.zeros((len(b), 6))
+    out[:, [0, 1, 2]] = b[:, [0, 1, 2]]
+    l, w, h, ry = b[:, [3]], b[:, [4]], b[:, [5]], b[:, [6]]
+    cos_ry, sin_ry = np.abs(np.cos(ry)), np.abs(np.sin(ry))
+    out[:, [3]] = l * cos_ry + w * sin_ry
+    out[:, [4]] = h
+    out[:, [5]] = w * cos_ry + l * sin_ry
+    return out
+
+
+def project_to_bev(anchors, bev_extents):
+    """-> (corners [x1, z1, x2, z2] in metres from the top-left of the BEV map, same normalised)."""
+    a = np.asarray(anchors)
+    x, z, hx, hz = a[:, 0], a[:, 2], a[:, 3] / 2.0, a[:, 5] / 2.0
+    x_min, x_max = bev_extents[0][0], bev_extents[0][1]
+    z_min, z_max = bev_extents[1][0], bev_extents[1][1]
+    corners = np.stack([x - hx, z_max - (z + hz), x + hx, z_max - (z - hz)], axis=1)
+    corners = corners - [x_min, z_min, x_min, z_min]
+    rng = [x_max - x_min, z_max - z_min, x_max - x_min, z_max - z_min]
+    return corners, corners / rng
+
+
+def project_to_image_space(anchors, stereo_calib_p2, image_shape):
+    """-> (corners [x1, y1, x2, y2] px, normalised corners), float32, from the 8 cuboid corners."""
+    a = np.asarray(anchors)
+    if a.shape[1] != 6:
+        raise ValueError("Invalid shape for anchors {}, should be (N, 6)".format(a.shape[1]))
+    x, y, z, dx, dy, dz = (a[:, k] for k in range(6))
+    hx, hz = dx / 2., dz / 2.
+    xc = np.array([x + hx, x + hx, x - hx, x - hx, x + hx, x + hx, x - hx, x - hx]).T.reshape(1, -1)
+    yc = np.array([y, y, y, y, y - dy, y - dy, y - dy, y - dy]).T.reshape(1, -1)
+    zc = np.array([z + hz, z - hz, z - hz, z + hz, z + hz, z - hz, z - hz, z + hz]).T.reshape(1, -1)
+    pts = np.vstack([xc, yc, zc])
+    p2d = np.dot(stereo_calib_p2, np.append(pts, np.ones((1, pts.shape[1])), axis=0))
+    u = (p2d[0] / p2d[2]).reshape(-1, 8)
+    v = (p2d[1] / p2d[2]).reshape(-1, 8)
+    corners = np.vstack([u.min(axis=1), v.min(axis=1), u.max(axis=1), v.max(axis=1)]).T
+    norm = corners / [image_shape[1], image_shape[0], image_shape[1], image_shape[0]]
+    return np.array(corners, dtype=np.float32), np.array(norm, dtype=np.float32)
+
+
+def offset_to_anchor(anchors, offsets):
+    a, o = np.asarray(anchors), np.asarray(offsets)
+    return np.stack((o[:, 0] * a[:, 3] + a[:, 0], o[:, 1] * a[:, 4] + a[:, 1],
+                     o[:, 2] * a[:, 5] + a[:, 2], np.exp(np.log(a[:, 3]) + o[:, 3]),
+                     np.exp(np.log(a[:, 4]) + o[:, 4]), np.exp(np.log(a[:, 5]) + o[:, 5])), axis=1)
+
+
+def reorder_projected_boxes(box_corners):
+    """[x1, y1, x2, y2] -> [y1, x1, y2, x2], the order tf.image.crop_and_resize wants."""
+    b = np.asarray(box_corners)
+    return np.stack([b[:, 1], b[:, 0], b[:, 3], b[:, 2]], axis=1)

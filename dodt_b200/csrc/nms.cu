@@ -1,0 +1,373 @@
+// S5 — greedy axis-aligned NMS with tf.image.non_max_suppression semantics, sm_100a.
+//
+// Semantics follow TensorFlow 1.3.0 core/kernels/non_max_suppression_op.cc, the op the reference
+// calls at avod/core/models/dt_rpn_model.py:587-591 (RPN: IoU 0.8, 1024/300 outputs) and
+// avod/core/models/dt_avod_model.py:609-613 (final: IoU 0.01, 100 outputs):
+//   - candidates are visited in order of decreasing score;
+//   - corners are normalised with min/max, area = (ymax-ymin)*(xmax-xmin), IoU = 0 if either area
+//     is <= 0, else inter / (area_i + area_j - inter), all in fp32 with IEEE division;
+//   - a candidate is dropped iff its IoU with an already selected box is > iou_threshold;
+//   - selection stops at min(max_output_size, n).
+// Equal scores are visited in ascending index order (a stable sort; TF's std::sort leaves that
+// unspecified).
+//
+// Greedy NMS is a sequential recurrence. It is evaluated here in windows of kWin score-sorted
+// candidates, one kernel launch per window:
+//   phase 1 (all CTAs)   64x64 tiles of pairwise IoU tests. For window candidate i the lanes of a
+//                        warp test 32 earlier candidates at a time and __ballot_sync packs the
+//                        results into the candidate's "suppressor" bitmask (bit j set iff j < i and
+//                        IoU(j, i) > thr); tiles against the boxes kept by earlier windows reduce
+//                        to one "dead on arrival" bit per candidate.
+//   phase 2 (last CTA to finish, classic threadfence hand-off — no CTA ever waits on another)
+//                        pulls the triangular bitmask into shared memory and solves the recurrence
+//                        by monotone relaxation: a candidate is KEPT once every suppressor is
+//                        known-removed, REMOVED once any suppressor is known-kept. Each sweep
+//                        decides at least the first undecided candidate, typical data needs a
+//                        handful of sweeps, and the fixed point is exactly the greedy result.
+//                        The kept prefix is cut at max_out, appended to the output and to the
+//                        kept-box list that later windows test against.
+// Windows after the one that completes the selection exit immediately.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace dodt {
+namespace {
+
+constexpr int kWin = 1536;             // candidates per window
+constexpr int kWords = kWin / 64;      // 24 bitmask words per window
+constexpr int kTriWords = 64 * (kWords * (kWords + 1) / 2);  // triangular suppressor store
+constexpr int kRoundThreads = 256;
+constexpr int kResolveThreads = kRoundThreads;
+
+struct NmsState {  // lives in the workspace, zeroed per call
+  int n_kept;      // boxes selected so far
+  int done;        // selection complete
+  unsigned tiles_done;  // CTA completion ticket of the current round
+  int pad;
+};
+
+struct NmsBox {
+  float ymin, xmin, ymax, xmax;
+};
+
+__device__ __forceinline__ bool iou_exceeds(const NmsBox &a, float area_a, const NmsBox &b,
+                                            float area_b, float thr) {
+  float iou = 0.0f;
+  if (area_a > 0.0f && area_b > 0.0f) {
+    const float iy0 = fmaxf(a.ymin, b.ymin), ix0 = fmaxf(a.xmin, b.xmin);
+    const float iy1 = fminf(a.ymax, b.ymax), ix1 = fminf(a.xmax, b.xmax);
+    const float inter = __fmul_rn(fmaxf(__fsub_rn(iy1, iy0), 0.0f), fmaxf(__fsub_rn(ix1, ix0), 0.0f));
+    if (inter > 0.0f)
+      iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  }
+  return iou > thr;
+}
+
+__global__ void __launch_bounds__(256)
+nms_iota(int *__restrict__ idx, int n) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) idx[i] = i;
+}
+
+// boxes in score order, corners normalised, plus areas
+__global__ void __launch_bounds__(256)
+nms_gather(const float *__restrict__ boxes, const int *__restrict__ order, int n,
+           NmsBox *__restrict__ sbox, float *__restrict__ sarea) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + __ldg(order + i));
+  NmsBox o;
+  o.ymin = fminf(b.x, b.z); o.xmin = fminf(b.y, b.w);
+  o.ymax = fmaxf(b.x, b.z); o.xmax = fmaxf(b.y, b.w);
+  sbox[i] = o;
+  sarea[i] = __fmul_rn(__fsub_rn(o.ymax, o.ymin), __fsub_rn(o.xmax, o.xmin));
+}
+
+// word offset of candidate i's suppressor words (words 0 .. i/64) in the triangular store
+__device__ __forceinline__ int tri_off(int i) {
+  const int bi = i >> 6;
+  return 64 * (bi * (bi + 1) / 2) + (i & 63) * (bi + 1);
+}
+
+__global__ void __launch_bounds__(kRoundThreads)
+nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
+          const int *__restrict__ order, int n, int base, int max_out, float thr,
+          unsigned long long *__restrict__ sup,      // [kTriWords] suppressor bitmasks
+          unsigned *__restrict__ dead,               // [kWin/32] killed by earlier windows
+          NmsBox *__restrict__ kbox, float *__restrict__ karea,  // kept boxes so far
+          NmsState *__restrict__ st, int *__restrict__ keep, int *__restrict__ n_keep) {
+  extern __shared__ unsigned long long smem_sup[];   // phase 2: [kTriWords]
+  __shared__ NmsBox jb[64];
+  __shared__ float ja[64];
+  __shared__ unsigned long long s_kept[kWords], s_removed[kWords];
+  __shared__ int s_prefix[kWords + 1];
+  __shared__ int s_last;
+
+  if (st->done) return;
+  const int wcount = min(kWin, n - base);          // candidates in this window
+  const int nb = (wcount + 63) >> 6;               // 64-blocks in this window
+  const int n_prev = st->n_kept;                   // boxes kept by earlier windows
+  const int pb = (n_prev + 63) >> 6;
+  const int tri_tiles = nb * (nb + 1) / 2;
+  const int n_tiles = tri_tiles + nb * pb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarps = kRoundThreads / 32;
+
+  // ---------------- phase 1: IoU tiles ----------------
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int bi, bj;          // candidate block, suppressor block
+    bool vs_prev;
+    if (tile < tri_tiles) {
+      // tile -> (bi, bj) with bj <= bi
+      bi = static_cast<int>((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
+      while (bi * (bi + 1) / 2 > tile) --bi;
+      while ((bi + 1) * (bi + 2) / 2 <= tile) ++bi;
+      bj = tile - bi * (bi + 1) / 2;
+      vs_prev = false;
+    } else {
+      const int t2 = tile - tri_tiles;
+      bi = t2 / pb;
+      bj = t2 % pb;
+      vs_prev = true;
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int j = bj * 64 + threadIdx.x;
+      if (vs_prev) {
+        const bool ok = j < n_prev;
+        jb[threadIdx.x] = ok ? kbox[j] : NmsBox{0.f, 0.f, 0.f, 0.f};
+        ja[threadIdx.x] = ok ? karea[j] : 0.0f;
+      } else {
+        const bool ok = j < wcount;
+        jb[threadIdx.x] = ok ? sbox[base + j] : NmsBox{0.f, 0.f, 0.f, 0.f};
+        ja[threadIdx.x] = ok ? sarea[base + j] : 0.0f;   // area 0 never suppresses
+      }
+    }
+    __syncthreads();
+    // each warp takes candidates i = bi*64 + warp, + kWarps, ...; lanes take suppressors j
+    for (int ii = warp; ii < 64; ii += kWarps) {
+      const int i = bi * 64 + ii;
+      if (i >= wcount) break;  // warp-uniform
+      const NmsBox b = sbox[base + i];
+      const float area = sarea[base + i];
+      const int jn = (vs_prev ? n_prev : wcount) - bj * 64;  // valid suppressors in this tile
+      bool h0 = lane < jn && iou_exceeds(jb[lane], ja[lane], b, area, thr);
+      bool h1 = lane + 32 < jn && iou_exceeds(jb[lane + 32], ja[lane + 32], b, area, thr);
+      if (!vs_prev && bj == bi) {  // diagonal tile: only earlier candidates suppress
+        h0 = h0 && lane < ii;
+        h1 = h1 && lane + 32 < ii;
+      }
+      const unsigned m0 = __ballot_sync(0xffffffffu, h0);
+      const unsigned m1 = __ballot_sync(0xffffffffu, h1);
+      if (lane == 0) {
+        if (vs_prev) {
+          if (m0 | m1) atomicOr(&dead[i >> 5], 1u << (i & 31));
+        } else {
+          sup[tri_off(i) + bj] = (static_cast<unsigned long long>(m1) << 32) | m0;
+        }
+      }
+    }
+  }
+
+  // ---------------- hand-off: the last CTA to finish runs phase 2 ----------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(&st->tiles_done, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // ---------------- phase 2: solve the window ----------------
+  const int used_words = 64 * (nb * (nb + 1) / 2);
+  for (int w = threadIdx.x; w < used_words; w += kResolveThreads) smem_sup[w] = __ldcg(sup + w);
+  if (threadIdx.x < kWords) {
+    const int w = threadIdx.x;
+    // bits beyond wcount and candidates killed by earlier windows start as removed
+    unsigned long long rem = (static_cast<unsigned long long>(__ldcg(dead + 2 * w + 1)) << 32) |
+                             __ldcg(dead + 2 * w);
+    const int valid = wcount - w * 64;
+    if (valid <= 0) rem = ~0ull;
+    else if (valid < 64) rem |= ~0ull << valid;
+    s_removed[w] = rem;
+    s_kept[w] = 0ull;
+  }
+  __syncthreads();
+
+  bool undecided[kWin / kResolveThreads];
+#pragma unroll
+  for (int q = 0; q < kWin / kResolveThreads; ++q) undecided[q] = true;
+  while (true) {
+    int pending = 0;
+#pragma unroll
+    for (int q = 0; q < kWin / kResolveThreads; ++q) {
+      const int i = q * kResolveThreads + threadIdx.x;
+      if (!undecided[q]) continue;
+      if (i >= wcount || ((s_removed[i >> 6] >> (i & 63)) & 1ull)) { undecided[q] = false; continue; }
+      const unsigned long long *row = smem_sup + tri_off(i);
+      const int bi = i >> 6;
+      bool hit_kept = false, all_removed = true;
+      for (int w = 0; w <= bi; ++w) {
+        const unsigned long long s = row[w];
+        if (s & s_kept[w]) { hit_kept = true; break; }
+        if (s & ~s_removed[w]) all_removed = false;
+      }
+      if (hit_kept) {
+        atomicOr(&s_removed[bi], 1ull << (i & 63));
+        undecided[q] = false;
+      } else if (all_removed) {
+        atomicOr(&s_kept[bi], 1ull << (i & 63));
+        undecided[q] = false;
+      } else {
+        pending = 1;
+      }
+    }
+    if (!__syncthreads_or(pending)) break;
+  }
+
+  // ---------------- emit: kept candidates in score order, cut at max_out ----------------
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 0; w < kWords; ++w) { s_prefix[w] = run; run += __popcll(s_kept[w]); }
+    s_prefix[kWords] = run;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < kWin / kResolveThreads; ++q) {
+    const int i = q * kResolveThreads + threadIdx.x;
+    if (i >= wcount) continue;
+    const unsigned long long kw = s_kept[i >> 6];
+    if (!((kw >> (i & 63)) & 1ull)) continue;
+    const int pos = n_prev + s_prefix[i >> 6] + __popcll(kw & ((1ull << (i & 63)) - 1ull));
+    if (pos < max_out) {
+      keep[pos] = order[base + i];
+      kbox[pos] = sbox[base + i];
+      karea[pos] = sarea[base + i];
+    }
+  }
+  // reset the per-round scratch for the next window
+  for (int w = threadIdx.x; w < kWin / 32; w += kResolveThreads) dead[w] = 0u;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int total = min(max_out, n_prev + s_prefix[kWords]);
+    st->n_kept = total;
+    st->tiles_done = 0u;
+    *n_keep = total;
+    if (total >= max_out || base + wcount >= n) st->done = 1;
+    __threadfence();
+  }
+}
+
+struct NmsLayout {
+  size_t keys_out, vals_in, vals_out, sbox, sarea, kbox, karea, sup, dead, state, cub, total;
+  size_t cub_bytes;
+};
+
+size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+int nms_layout(int64_t n, NmsLayout *L) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  const size_t nn = static_cast<size_t>(n > 0 ? n : 1);
+  L->keys_out = take(nn * 4);
+  L->vals_in = take(nn * 4);
+  L->vals_out = take(nn * 4);
+  L->sbox = take(nn * sizeof(NmsBox));
+  L->sarea = take(nn * 4);
+  L->kbox = take(nn * sizeof(NmsBox));
+  L->karea = take(nn * 4);
+  L->sup = take(static_cast<size_t>(kTriWords) * 8);
+  L->dead = take(kWin / 32 * 4);
+  L->state = take(sizeof(NmsState));
+  size_t cub_bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(
+      nullptr, cub_bytes, static_cast<const float *>(nullptr), static_cast<float *>(nullptr),
+      static_cast<const int *>(nullptr), static_cast<int *>(nullptr), static_cast<int>(nn));
+  if (e != cudaSuccess) {
+    // no device (CPU-only host querying a size): CUB's size query needs none in practice, but
+    // stay conservative if it ever does
+    (void)cudaGetLastError();
+    cub_bytes = nn * 16 + (1u << 20);
+  }
+  L->cub_bytes = cub_bytes;
+  L->cub = take(cub_bytes);
+  L->total = off;
+  return DODT_OK;
+}
+
+}  // namespace
+}  // namespace dodt
+
+extern "C" {
+
+size_t dodt_nms_workspace_bytes(int64_t n) {
+  if (n < 0 || n > 0x7FFFFFFF) return 0;
+  dodt::NmsLayout L;
+  dodt::nms_layout(n, &L);
+  return L.total;
+}
+
+int dodt_nms(const float *boxes, const float *scores, int64_t n, int32_t max_out,
+             float iou_threshold, int32_t *keep, int32_t *n_keep, void *workspace,
+             size_t workspace_bytes, dodt_stream_t stream_) {
+  using namespace dodt;
+  if (n < 0 || n > 0x7FFFFFFF || max_out < 0 || !n_keep || (max_out > 0 && !keep)) return DODT_EINVAL;
+  if (n > 0 && (!boxes || !scores)) return DODT_EINVAL;
+  if (reinterpret_cast<uintptr_t>(boxes) % 16 != 0) return DODT_EALIGN;
+  cudaStream_t stream = as_stream(stream_);
+  DODT_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t), stream));
+  if (max_out > 0) DODT_CUDA_TRY(cudaMemsetAsync(keep, 0xFF, sizeof(int32_t) * max_out, stream));
+  if (n == 0 || max_out == 0) return DODT_OK;
+  NmsLayout L;
+  nms_layout(n, &L);
+  if (!workspace || workspace_bytes < L.total) return DODT_ECAPACITY;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return DODT_EALIGN;
+  char *ws = static_cast<char *>(workspace);
+  float *keys_out = reinterpret_cast<float *>(ws + L.keys_out);
+  int *vals_in = reinterpret_cast<int *>(ws + L.vals_in);
+  int *order = reinterpret_cast<int *>(ws + L.vals_out);
+  NmsBox *sbox = reinterpret_cast<NmsBox *>(ws + L.sbox);
+  float *sarea = reinterpret_cast<float *>(ws + L.sarea);
+  NmsBox *kbox = reinterpret_cast<NmsBox *>(ws + L.kbox);
+  float *karea = reinterpret_cast<float *>(ws + L.karea);
+  unsigned long long *sup = reinterpret_cast<unsigned long long *>(ws + L.sup);
+  unsigned *dead = reinterpret_cast<unsigned *>(ws + L.dead);
+  NmsState *st = reinterpret_cast<NmsState *>(ws + L.state);
+
+  const int ni = static_cast<int>(n);
+  // dead bits and state start at zero (one memset: they are adjacent up to alignment padding)
+  DODT_CUDA_TRY(cudaMemsetAsync(ws + L.dead, 0, (L.state - L.dead) + sizeof(NmsState), stream));
+  nms_iota<<<ceil_div(ni, 256), 256, 0, stream>>>(vals_in, ni);
+  DODT_AFTER_LAUNCH();
+  size_t cub_bytes = L.cub_bytes;
+  DODT_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(ws + L.cub, cub_bytes, scores, keys_out,
+                                                          vals_in, order, ni, 0, 32, stream));
+  count_launch(4);  // CUB's histogram + onesweep passes (library kernels)
+  nms_gather<<<ceil_div(ni, 256), 256, 0, stream>>>(boxes, order, ni, sbox, sarea);
+  DODT_AFTER_LAUNCH();
+
+  const size_t smem = static_cast<size_t>(kTriWords) * sizeof(unsigned long long);
+  static bool attr_set = false;  // per process; the attribute is a property of the function
+  if (!attr_set) {
+    DODT_CUDA_TRY(cudaFuncSetAttribute(nms_round, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    attr_set = true;
+  }
+  for (int base = 0; base < ni; base += kWin) {
+    const int wcount = ni - base < kWin ? ni - base : kWin;
+    const int nb = (wcount + 63) / 64;
+    const int pb = (max_out + 63) / 64;  // upper bound of kept blocks from earlier windows
+    int tiles = nb * (nb + 1) / 2 + (base > 0 ? nb * pb : 0);
+    const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
+    nms_round<<<grid, kRoundThreads, smem, stream>>>(sbox, sarea, order, ni, base, max_out,
+                                                     iou_threshold, sup, dead, kbox, karea, st,
+                                                     keep, n_keep);
+    DODT_AFTER_LAUNCH();
+  }
+  return DODT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+"""Tensor-level wrappers of the C ABI (include/dodt_fe.h): torch CUDA tensors in, torch CUDA tensors
+out, work enqueued on torch's current stream. PyTorch is used for device memory and streams only;
+every computation happens in libdodt_fe.so. No CPU path exists: inputs must live on a CUDA device.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (BEV_STATS_LEN, DODT_F32, DODT_F64, MAX_DENSITY_LUT, MAX_SLICES, BevParams,
+                   check, load)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dodt_b200 runs on CUDA tensors only (there is no CPU fallback)")
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return DODT_F32
+    if t.dtype == torch.float64:
+        return DODT_F64
+    raise TypeError("expected a float32 or float64 tensor, got %s" % t.dtype)
+
+
+def launch_count():
+    return int(load().dodt_launch_count())
+
+
+# ------------------------------------------------------------------------------------------ S1
+
+
+def bev_grid(area_extents, voxel_size):
+    """(nx, ny, nz, min_x, min_y, min_z) of wavedata voxel_grid_2d.py:125-130,142-143."""
+    ext = (ctypes.c_double * 6)(*[float(v) for v in np.asarray(area_extents, dtype=np.float64).reshape(6)])
+    grid = (ctypes.c_int32 * 6)()
+    check(load().dodt_bev_grid(ext, float(voxel_size), grid), "dodt_bev_grid")
+    return tuple(int(v) for v in grid)
+
+
+def density_lut(norm_value):
+    """min(1, log(n + 1) / norm) for n = 0.. until it saturates, computed with NumPy's log so that
+    the density map is bit-identical to avod/core/bev_generators/bev_generator.py:34-35."""
+    n = np.arange(MAX_DENSITY_LUT + 1)
+    vals = np.minimum(1.0, np.log(n + 1) / norm_value)
+    sat = np.flatnonzero(vals >= 1.0)
+    if len(sat) == 0 or sat[0] > MAX_DENSITY_LUT:
+        raise ValueError("density norm_value %r needs more than %d LUT entries" %
+                         (norm_value, MAX_DENSITY_LUT))
+    return vals[:sat[0]]
+
+
+def make_bev_params(ground_plane, area_extents, voxel_size, height_lo, height_hi, num_slices,
+                    filter_mode=True, occ_lo=0.2, occ_hi=2.0, norm_value=np.log(16)):
+    if not 0 <= int(num_slices) <= MAX_SLICES:
+        raise ValueError("num_slices must be in [0, %d]" % MAX_SLICES)
+    p = BevParams()
+    plane = [0.0, 0.0, 0.0, 0.0] if ground_plane is None else [float(v) for v in ground_plane]
+    if len(plane) != 4:
+        raise ValueError("ground_plane must have 4 coefficients")
+    ext = np.asarray(area_extents, dtype=np.float64).reshape(-1)
+    if ext.shape != (6,):
+        raise ValueError("Extents are the wrong shape {}".format(np.asarray(area_extents).shape))
+    p.plane[:] = plane
+    p.extents[:] = [float(v) for v in ext]
+    p.voxel_size = float(voxel_size)
+    p.height_lo = float(height_lo)
+    p.height_hi = float(height_hi)
+    p.num_slices = int(num_slices)
+    p.filter_mode = 1 if filter_mode else 0
+    p.occ_lo = float(occ_lo)
+    p.occ_hi = float(occ_hi)
+    lut = density_lut(norm_value)
+    p.density_lut_len = len(lut)
+    for i, v in enumerate(lut):
+        p.density_lut[i] = float(v)
+    return p
+
+
+def bev_workspace_bytes(n_points, num_slices, nx, nz):
+    return int(load().dodt_bev_workspace_bytes(int(n_points), int(num_slices), int(nx), int(nz)))
+
+
+def bev_slices(points, params, maps, occ, stats, workspace, winner_idx=None, counts=None):
+    """points (3, N) CUDA f32/f64 with unit inner stride. Fills maps [(S+1), nz, nx] f32,
+    occ [nx, nz] u8 (or None), stats [24] i32."""
+    _need_cuda(points, maps, occ, stats, workspace, winner_idx, counts)
+    if points.dim() != 2 or points.shape[0] != 3:
+        raise ValueError("Points have the wrong shape: {}".format(tuple(points.shape)))
+    n = points.shape[1]
+    if n > 0 and points.stride(1) != 1:
+        raise ValueError("points rows must be contiguous")
+    row_stride = points.stride(0) if n > 0 else 0
+    rc = load().dodt_bev_slices(_ptr(points), _dtype_code(points), n, max(row_stride, n),
+                                ctypes.byref(params), _ptr(maps), _ptr(occ), _ptr(stats),
+                                _ptr(winner_idx), _ptr(counts), _ptr(workspace),
+                                workspace.numel() * workspace.element_size(), _stream())
+    check(rc, "dodt_bev_slices")
+
+
+# ------------------------------------------------------------------------------------------ S2
+
+
+def integral_workspace_bytes(nx, nz):
+    return int(load().dodt_integral_workspace_bytes(int(nx), int(nz)))
+
+
+def integral_image_2d(occ, ii=None, workspace=None):
+    """occ [nx, nz] u8 -> ii [(nx+1), (nz+1)] i32 (wavedata integral_image_2d.py:17-37)."""
+    _need_cuda(occ, ii, workspace)
+    if occ.dim() != 2:
+        raise ValueError("Not a 2D image for integral image: input dim {}".format(occ.dim()))
+    if occ.dtype != torch.uint8 or not occ.is_contiguous():
+        raise TypeError("occupancy grid must be a contiguous uint8 tensor")
+    nx, nz = occ.shape
+    if ii is None:
+        ii = torch.empty((nx + 1, nz + 1), dtype=torch.int32, device=occ.device)
+    if workspace is None:
+        workspace = torch.empty(integral_workspace_bytes(nx, nz), dtype=torch.uint8, device=occ.device)
+    check(load().dodt_integral_image_2d(_ptr(occ), nx, nz, _ptr(ii), _ptr(workspace),
+                                        workspace.numel(), _stream()), "dodt_integral_image_2d")
+    return ii
+
+
+def map_to_index(coords, voxel_size, min_x, min_z, nx, nz):
+    """coords (n, 2) f32/f64 CUDA -> (n, 2) i32 (wavedata voxel_grid_2d.py:162-186)."""
+    _need_cuda(coords)
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    out = torch.empty((n, 2), dtype=torch.int32, device=coords.device)
+    check(load().dodt_map_to_index(_ptr(coords), _dtype_code(coords), n, float(voxel_size), min_x,
+                                   min_z, nx, nz, _ptr(out), _stream()), "dodt_map_to_index")
+    return out
+
+
+def anchor_filter_2d(anchors, ii, nx, nz, min_x, min_z, voxel_size, density_threshold=1,
+                     keep=None, scores=None):
+    """anchors (n, 6) f32/f64 CUDA, ii from integral_image_2d -> keep (n,) u8."""
+    _need_cuda(anchors, ii, keep, scores)
+    if anchors.dim() != 2 or anchors.shape[1] != 6:
+        raise TypeError("Given input does not have valid number of attributes. "
+                        "Should be N x 6 for anchor.")
+    anchors = anchors.contiguous()
+    n = anchors.shape[0]
+    if keep is None:
+        keep = torch.empty((n,), dtype=torch.uint8, device=anchors.device)
+    check(load().dodt_anchor_filter_2d(_ptr(anchors), _dtype_code(anchors), n, _ptr(ii), nx, nz,
+                                       min_x, min_z, float(voxel_size), float(density_threshold),
+                                       _ptr(keep), _ptr(scores), _stream()),
+          "dodt_anchor_filter_2d")
+    return keep
+
+
+# ------------------------------------------------------------------------------------------ S3
+
+
+def crop_and_resize(image, boxes, box_ind, crop_size, extrapolation_value=0.0, out=None):
+    """image [B,H,W,C] f32 NHWC, boxes [n,4] f32, box_ind [n] i32 -> [n, ch, cw, C] f32."""
+    _need_cuda(image, boxes, box_ind, out)
+    if image.dim() != 4:
+        raise ValueError("image must be 4-D [batch, height, width, channels]")
+    if boxes.dim() != 2 or boxes.shape[1] != 4:
+        raise ValueError("boxes must be 2-D [num_boxes, 4]")
+    if box_ind.dim() != 1 or box_ind.shape[0] != boxes.shape[0]:
+        raise ValueError("box_ind must be 1-D with one entry per box")
+    ch, cw = int(crop_size[0]), int(crop_size[1])
+    if ch <= 0 or cw <= 0:
+        raise ValueError("crop dimensions must be positive")
+    image = image.contiguous()
+    boxes = boxes.contiguous()
+    box_ind = box_ind.contiguous()
+    if image.dtype != torch.float32 or boxes.dtype != torch.float32 or box_ind.dtype != torch.int32:
+        raise TypeError("crop_and_resize expects float32 image/boxes and int32 box_ind")
+    B, H, W, C = image.shape
+    n = boxes.shape[0]
+    if out is None:
+        # rows with an out-of-range box_ind are left untouched by TF; give them a defined value
+        out = torch.zeros((n, ch, cw, C), dtype=torch.float32, device=image.device) \
+            if n and bool(((box_ind < 0) | (box_ind >= B)).any()) \
+            else torch.empty((n, ch, cw, C), dtype=torch.float32, device=image.device)
+    check(load().dodt_crop_and_resize(_ptr(image), B, H, W, C, _ptr(boxes), _ptr(box_ind), n, ch,
+                                      cw, float(extrapolation_value), _ptr(out), _stream()),
+          "dodt_crop_and_resize")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ S4
+
+
+def correlation_out_shape(H, W, kernel_size, max_displacement, stride_1, stride_2, pad):
+    hwc = (ctypes.c_int32 * 3)()
+    rc = load().dodt_correlation_out_shape(H, W, kernel_size, max_displacement, stride_1, stride_2,
+                                           pad, hwc)
+    if rc == _lib.DODT_ESHAPE:
+        raise ValueError("Neighborhood and kernel don't fit in input.")
+    check(rc, "dodt_correlation_out_shape")
+    return int(hwc[0]), int(hwc[1]), int(hwc[2])
+
+
+def correlation(a, b, kernel_size, max_displacement, stride_1, stride_2, pad, out=None):
+    _need_cuda(a, b, out)
+    if a.dim() != 4:
+        raise ValueError("input_a must have rank 4")
+    if b.dim() != 4:
+        raise ValueError("input_b must have rank 4")
+    if a.shape != b.shape:
+        raise ValueError("input_a and input_b must have the same shape")
+    if kernel_size % 2 == 0:
+        raise ValueError("kernel_size must be odd")
+    if a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise TypeError("correlation expects float32 inputs")
+    a = a.contiguous()
+    b = b.contiguous()
+    N, H, W, C = a.shape
+    oh, ow, oc = correlation_out_shape(H, W, kernel_size, max_displacement, stride_1, stride_2, pad)
+    if out is None:
+        out = torch.empty((N, oh, ow, oc), dtype=torch.float32, device=a.device)
+    check(load().dodt_correlation(_ptr(a), _ptr(b), N, H, W, C, kernel_size, max_displacement,
+                                  stride_1, stride_2, pad, _ptr(out), _stream()),
+          "dodt_correlation")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ S5
+
+
+def nms_workspace_bytes(n):
+    return int(load().dodt_nms_workspace_bytes(int(n)))
+
+
+def nms(boxes, scores, max_out, iou_threshold, keep=None, n_keep=None, workspace=None):
+    """boxes [n,4] f32, scores [n] f32 -> (keep [max_out] i32 padded with -1, n_keep [1] i32),
+    both on the device (no synchronisation)."""
+    _need_cuda(boxes, scores, keep, n_keep, workspace)
+    if boxes.dim() != 2 or boxes.shape[1] != 4:
+        raise ValueError("boxes must be 2-D [num_boxes, 4]")
+    if scores.dim() != 1 or scores.shape[0] != boxes.shape[0]:
+        raise ValueError("scores has incompatible shape")
+    if boxes.dtype != torch.float32 or scores.dtype != torch.float32:
+        raise TypeError("non_max_suppression expects float32 boxes and scores")
+    boxes = boxes.contiguous()
+    scores = scores.contiguous()
+    n = boxes.shape[0]
+    max_out = int(max_out)
+    if max_out < 0:
+        raise ValueError("max_output_size must be non-negative")
+    dev = boxes.device
+    if keep is None:
+        keep = torch.empty((max_out,), dtype=torch.int32, device=dev)
+    if n_keep is None:
+        n_keep = torch.empty((1,), dtype=torch.int32, device=dev)
+    if workspace is None:
+        workspace = torch.empty(max(nms_workspace_bytes(n), 256), dtype=torch.uint8, device=dev)
+    check(load().dodt_nms(_ptr(boxes), _ptr(scores), n, max_out, float(iou_threshold), _ptr(keep),
+                          _ptr(n_keep), _ptr(workspace), workspace.numel(), _stream()), "dodt_nms")
+    return keep, n_keep

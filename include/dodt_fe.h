@@ -1,0 +1,186 @@
+/*
+ * dodt_fe.h — C ABI of libdodt_fe.so, the B200 (sm_100a) implementation of the DODT/AVOD
+ * per-frame proposal front end:
+ *
+ *   S1  LiDAR points -> BEV height-slice + density maps   (dodt_bev_slices)
+ *   S2  integral image + empty-anchor filter               (dodt_integral_image_2d,
+ *                                                           dodt_anchor_filter_2d, dodt_map_to_index)
+ *   S3  crop_and_resize of NHWC feature maps               (dodt_crop_and_resize)
+ *   S4  inter-frame feature correlation (forward)          (dodt_correlation)
+ *   S5  greedy axis-aligned NMS                            (dodt_nms)
+ *
+ * Conventions (precedent: the reference's only FFI, the ctypes binding of
+ * wavedata/wavedata/tools/core/lib/src/integral_images_3d.cpp:66-77 loaded by
+ * wavedata/wavedata/tools/core/integral_image.py:96-120 — caller-allocated outputs, plain
+ * pointers and sizes, no ownership transfer):
+ *
+ *  - every data pointer is a DEVICE pointer unless the parameter comment says "host";
+ *  - the caller owns every buffer including workspaces; the library never allocates or frees
+ *    device memory and keeps no state between calls (re-entrant, one host thread per GPU);
+ *  - every compute entry point enqueues work on `stream` (a cudaStream_t passed as void*)
+ *    and returns without synchronising; all of them are CUDA-graph capturable;
+ *  - return value: DODT_OK (0) or a negative DODT_E* code; nothing is printed;
+ *  - there is no CPU fallback: without a CUDA device the compute entry points return DODT_ECUDA.
+ *
+ * Reference paths are relative to the Guoxs/DODT checkout.
+ */
+#ifndef DODT_FE_H_
+#define DODT_FE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DODT_FE_VERSION 100 /* major*100 + minor */
+
+typedef void *dodt_stream_t; /* cudaStream_t */
+
+enum dodt_status {
+  DODT_OK = 0,
+  DODT_EINVAL = -1,    /* bad argument value (NULL pointer, negative size, even kernel_size, ...) */
+  DODT_ESHAPE = -2,    /* shapes inconsistent / output would be empty                              */
+  DODT_ECAPACITY = -3, /* workspace too small or size beyond what the packed keys can index        */
+  DODT_ECUDA = -4,     /* a CUDA runtime call failed; see dodt_last_cuda_error()                   */
+  DODT_EALIGN = -5     /* pointer not aligned as documented                                        */
+};
+
+enum dodt_dtype { DODT_F32 = 0, DODT_F64 = 1 };
+
+#define DODT_MAX_SLICES 15
+#define DODT_MAX_DENSITY_LUT 64
+/* layout of the int32 stats block written by dodt_bev_slices */
+#define DODT_BEV_STATS_LEN 24
+#define DODT_BEV_STAT_DENSITY 16  /* number of points inside the density slice                    */
+#define DODT_BEV_STAT_OCC 17      /* number of points inside the occupancy (anchor filter) slice  */
+#define DODT_BEV_STAT_TOUCHED 18  /* number of (map, cell) pairs touched by at least one point    */
+#define DODT_BEV_STAT_OVERFLOW 19 /* !=0: touched list overflowed the workspace (result invalid)  */
+#define DODT_BEV_STAT_OOB 20      /* number of points binned outside the grid (no-filter mode)    */
+
+const char *dodt_strerror(int code);
+const char *dodt_last_cuda_error(void); /* thread-local text of the last CUDA failure */
+int dodt_version(void);
+/* number of kernels this library has launched from the calling thread since load
+ * (memset nodes are not counted); used by bench.py for its "gpu_launches" claim */
+int64_t dodt_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * S1 — BEV height-slice + density maps, with the S2 occupancy grid produced in the same pass.
+ * Replaces avod/core/bev_generators/bev_slices.py:33-150 (BevSlices.generate_bev), which calls
+ * avod/datasets/kitti/kitti_utils.py:81-109 (create_slice_filter),
+ * wavedata/wavedata/tools/obj_detection/obj_utils.py:453-500 (get_point_filter),
+ * wavedata/wavedata/tools/core/voxel_grid_2d.py:43-160 (VoxelGrid2D.voxelize_2d),
+ * wavedata/wavedata/tools/core/geometry_utils.py:25-40 (dist_to_plane) and
+ * avod/core/bev_generators/bev_generator.py:23-41 (_create_density_map); the occupancy grid
+ * replaces avod/datasets/kitti/kitti_utils.py:212-277 (_apply_slice_filter +
+ * create_sliced_voxel_grid_2d, leaf_layout_2d).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct dodt_bev_params {
+  double plane[4];     /* ground plane a,b,c,d                                                    */
+  double extents[6];   /* x_min,x_max,y_min,y_max,z_min,z_max (open intervals, obj_utils.py:474)  */
+  double voxel_size;   /* the fp32-rounded proto value, e.g. (double)0.1f                          */
+  double height_lo;    /* BevSlices config (bev_slices.py:24-31)                                  */
+  double height_hi;
+  int32_t num_slices;  /* 0..DODT_MAX_SLICES                                                      */
+  int32_t filter_mode; /* 1: slice filters as in generate_bev; 0: every point belongs to slice 0
+                          and to the density map (plain VoxelGrid2D.voxelize_2d of given points)  */
+  double occ_lo;       /* occupancy slice above the plane, kitti_utils.py:212-213 (0.2 .. 2.0)    */
+  double occ_hi;
+  int32_t density_lut_len;                   /* entries used in density_lut, <= 64                */
+  int32_t reserved;
+  double density_lut[DODT_MAX_DENSITY_LUT];  /* density value for n points, n < lut_len; 1.0 for
+                                                n >= lut_len (min(1, log(n+1)/norm))              */
+} dodt_bev_params;
+
+/* grid[0..5] = nx, ny, nz, min_x, min_y, min_z in voxel units: floor(ext_min/voxel) and
+ * ceil(ext_max/voxel - 1) as voxel_grid_2d.py:125-130,142-143 (ny is the number of y bins, used
+ * only for the winner key; the grid itself is collapsed along y). Host only. */
+int dodt_bev_grid(const double extents[6], double voxel_size, int32_t grid[6]);
+
+size_t dodt_bev_workspace_bytes(int64_t n_points, int32_t num_slices, int32_t nx, int32_t nz);
+
+/*
+ * pts       : (3, n) structure-of-arrays as the reference passes it (point_cloud (3,N)); element
+ *             type pts_dtype; row r starts at pts + r*row_stride elements.
+ * maps      : out float32 [(num_slices+1), nz, nx]; maps[s] is height map s already rotated as
+ *             bev_slices.py:115-116 (row 0 = far z), maps[num_slices] is the density map.
+ * occ       : out uint8 [nx, nz] (1 = VOXEL_FILLED, 0 = VOXEL_EMPTY) or NULL to skip.
+ * stats     : out int32 [DODT_BEV_STATS_LEN]; stats[s] = points in height slice s.
+ * winner_idx: optional out int32 [num_slices, nz, nx] — index of the winning point per cell
+ *             (-1 = empty); NULL to skip (parity/diagnostic output, integer exact).
+ * counts    : optional out int32 [nz, nx] — points per cell of the density slice; NULL to skip.
+ */
+int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, int64_t row_stride,
+                    const dodt_bev_params *params /* host */, float *maps, uint8_t *occ,
+                    int32_t *stats, int32_t *winner_idx, int32_t *counts, void *workspace,
+                    size_t workspace_bytes, dodt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * S2 — integral image of the occupancy grid and the O(1) box-sum anchor filter.
+ * Replaces wavedata/wavedata/tools/core/integral_image_2d.py:7-87 (IntegralImage2D),
+ * wavedata/wavedata/tools/core/voxel_grid_2d.py:162-186 (map_to_index) and
+ * avod/core/anchor_filter.py:64-119 (get_empty_anchor_filter_2d).
+ * ---------------------------------------------------------------------------------------- */
+size_t dodt_integral_workspace_bytes(int32_t nx, int32_t nz);
+
+/* ii: out int32 [(nx+1), (nz+1)], zero first row/column (integral_image_2d.py:30-37) */
+int dodt_integral_image_2d(const uint8_t *occ, int32_t nx, int32_t nz, int32_t *ii,
+                           void *workspace, size_t workspace_bytes, dodt_stream_t stream);
+
+/* coords (n,2) [x,z] of dtype -> idx int32 (n,2); division in the coordinate dtype, truncation
+ * toward zero, shift by the grid minimum, clip to [0, ndiv] (voxel_grid_2d.py:182-184) */
+int dodt_map_to_index(const void *coords, int32_t dtype, int64_t n, double voxel_size,
+                      int32_t min_x, int32_t min_z, int32_t nx, int32_t nz, int32_t *idx,
+                      dodt_stream_t stream);
+
+/* anchors (n,6) [x,y,z,dim_x,dim_y,dim_z] row-major of dtype; keep: out uint8 [n];
+ * scores: optional out int32 [n] box sums (NULL to skip) */
+int dodt_anchor_filter_2d(const void *anchors, int32_t dtype, int64_t n, const int32_t *ii,
+                          int32_t nx, int32_t nz, int32_t min_x, int32_t min_z, double voxel_size,
+                          double density_threshold, uint8_t *keep, int32_t *scores,
+                          dodt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * S3 — tf.image.crop_and_resize (TensorFlow 1.3.0 core/kernels/crop_and_resize_op.cc, bilinear),
+ * called at avod/core/models/dt_rpn_model.py:418-428 and dt_avod_model.py:253-273.
+ * image [batch,H,W,C] f32 NHWC; boxes [n,4] normalised [y1,x1,y2,x2]; box_ind [n] (rows whose
+ * index is outside [0,batch) are left untouched, as TF does); crops out [n,crop_h,crop_w,C].
+ * ---------------------------------------------------------------------------------------- */
+int dodt_crop_and_resize(const float *image, int32_t batch, int32_t height, int32_t width,
+                         int32_t channels, const float *boxes, const int32_t *box_ind, int64_t n,
+                         int32_t crop_h, int32_t crop_w, float extrapolation_value, float *crops,
+                         dodt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * S4 — FlowNet correlation forward. Replaces the TF custom op
+ * avod/core/ops/correlation/correlation_op.cc:53-62 (REGISTER_OP "Correlation"),
+ * correlation_kernel.cc:26-124 (shape math, padding) and correlation_kernel.cu.cc:21-119
+ * (CorrelateData) + pad.cu.cc:14-74 (PadData; padding is never materialised here).
+ * a, b [batch,H,W,C] f32 NHWC -> out [batch,out_h,out_w,(2*(max_disp/stride_2)+1)^2].
+ * ---------------------------------------------------------------------------------------- */
+int dodt_correlation_out_shape(int32_t height, int32_t width, int32_t kernel_size,
+                               int32_t max_displacement, int32_t stride_1, int32_t stride_2,
+                               int32_t pad, int32_t out_hwc[3]);
+int dodt_correlation(const float *a, const float *b, int32_t batch, int32_t height, int32_t width,
+                     int32_t channels, int32_t kernel_size, int32_t max_displacement,
+                     int32_t stride_1, int32_t stride_2, int32_t pad, float *out,
+                     dodt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * S5 — tf.image.non_max_suppression (TensorFlow 1.3.0 core/kernels/non_max_suppression_op.cc),
+ * called at avod/core/models/dt_rpn_model.py:587-591 and dt_avod_model.py:609-613.
+ * boxes [n,4] f32 (any corner order), scores [n] f32; keep: out int32 [max_out] (entries past
+ * *n_keep are set to -1); n_keep: out int32 [1] on the device; suppress iff IoU > iou_threshold.
+ * Equal scores are ordered by ascending index (TF leaves that order unspecified).
+ * ---------------------------------------------------------------------------------------- */
+size_t dodt_nms_workspace_bytes(int64_t n);
+int dodt_nms(const float *boxes, const float *scores, int64_t n, int32_t max_out,
+             float iou_threshold, int32_t *keep, int32_t *n_keep, void *workspace,
+             size_t workspace_bytes, dodt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DODT_FE_H_ */
