@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Headline benchmark: frames/s of the DODT proposal front end (BEV maps + anchor filter + crops +
+correlation + NMS) on N B200s, with the HBM roofline of the dominant kernel and the CPU baseline.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU oracle arm)
+
+A "step" is one frame of BASELINE.json configs[1] (KITTI car config: 120k-point cloud -> 6 BEV maps
+and occupancy, 89 600-anchor filter, 3x3 RPN crops, NMS 0.8/1024, tau=1 BEV-feature correlation,
+7x7 crops of BEV/image/correlation maps for 1024 proposals, NMS 0.01/100) on synthetic
+KITTI-shaped data. `value` is timed with every input resident in HBM (CUDA-graph replay per frame,
+three resident frame slots cycled so that each step reads > 200 MB of inputs the previous step did
+not touch); `e2e` re-times the same steps through the public Python API with all inputs in pinned
+host memory, H2D and D2H inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIG_ID = 2   # BASELINE.json configs[1]
+WORKLOAD = ("configs[1] KITTI car config + tau=1 correlation: 120k pts -> BEV 700x800x6, "
+            "89600-anchor filter, 3x3 RPN crops, NMS(0.8,1024), corr 700x800x32->25, "
+            "7x7 crops x(32+32+25)ch x1024, NMS(0.01,100)")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--slots", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm (oracle): --impl reference and the cpu_baseline object
+# --------------------------------------------------------------------------------------------
+
+def cpu_arm(steps, warmup, workers):
+    """Each step = `workers` frames run concurrently, one frame per process (the reference's own
+    parallelism is os.fork over sample indices, scripts/preprocessing/gen_tracking_mini_batches.py:48-69)."""
+    import multiprocessing as mp
+    from oracle import build_oracle, cpu_frontend
+    build_oracle.build()
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        frame = 0
+        for _ in range(warmup):
+            pool.map(cpu_frontend._worker, [(CONFIG_ID, frame + i) for i in range(workers)])
+            frame += workers
+        t0 = time.perf_counter()
+        compute_s = 0.0
+        stage = {}
+        for _ in range(steps):
+            res = pool.map(cpu_frontend._worker, [(CONFIG_ID, frame + i) for i in range(workers)])
+            frame += workers
+            compute_s += max(r[0] for r in res)
+            for r in res:
+                for k, v in r[1].items():
+                    stage[k] = stage.get(k, 0.0) + v
+        wall = time.perf_counter() - t0
+    n_frames = steps * workers
+    # frames/s of the front end itself: input synthesis inside the workers is not counted
+    return dict(fps=n_frames / compute_s, wall_s=wall, compute_s=compute_s, frames=n_frames,
+                stage_ms={k: 1e3 * v / n_frames for k, v in stage.items()})
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 16))
+    steps = max(1, min(args.steps, 6))       # bounded: a CPU frame takes seconds
+    warmup = min(args.warmup, 1)
+    r = cpu_arm(steps, warmup, workers)
+    line = {
+        "impl": "reference", "metric": "front-end frames/sec", "value": r["fps"], "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * r["compute_s"] / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": "%d frames in parallel, one per process" % workers},
+        "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": workers, "kind": "port",
+                         "sample": "%d frames (%d steps x %d processes); S1/S2 NumPy restatement of "
+                                   "the reference's NumPy, S3/S4/S5 C restatement" %
+                                   (r["frames"], steps, workers),
+                         "stage_ms_per_frame": r["stage_ms"]},
+        "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from dodt_b200 import ops
+    from dodt_b200.frontend import FrontEnd
+    from dodt_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the front end has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    fe = FrontEnd()
+    n_slots = max(2, args.slots)
+    slots = [fe.new_slot() for _ in range(n_slots)]
+    # one KITTI-tracking-shaped stream per GPU: rank r reads frames of "sequence" r
+    host_inputs = []
+    for i in range(n_slots):
+        inp = synth.frame_inputs(CONFIG_ID, 1000 * rank + i)
+        pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in inp.items()}
+        host_inputs.append(pinned)
+    n_points = host_inputs[0]["points"].shape[1]
+
+    def upload(slot, pinned):
+        for k, dst in slot.input_tensors().items():
+            src = pinned[k]
+            if k == "points":
+                dst[:, :src.shape[1]].copy_(src, non_blocking=True)
+                slot.n_points = src.shape[1]
+            else:
+                dst.copy_(src, non_blocking=True)
+
+    for s_, p in zip(slots, host_inputs):
+        upload(s_, p)
+    torch.cuda.synchronize()
+    graphs, launches = [], 0
+    for i in range(n_slots):
+        g, launches = fe.capture(slots[i], slots[i - 1])
+        graphs.append(g)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ value: device-resident
+    K, Wm = args.steps, max(args.warmup, 3)
+    for i in range(Wm):
+        graphs[i % n_slots].replay()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gathered = None
+    barrier()
+    ev0.record()
+    for i in range(K):
+        graphs[i % n_slots].replay()
+    if world > 1:
+        # the only collective of the path: per-shard detection lists
+        last = slots[(K - 1) % n_slots]
+        payload = torch.cat([last.top_idx, last.n_top, last.final_idx, last.n_final])
+        gathered = [torch.empty_like(payload) for _ in range(world)]
+        dist.all_gather(gathered, payload)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    fps = K * world / (ms_max / 1e3)
+
+    # ------------------------------------------------------------------ per-stage + dominant kernel
+    c = fe.cfg
+    reps = max(20, min(K, 100))
+
+    def time_stage(fn):
+        for i in range(3):
+            fn(slots[i % n_slots], slots[(i - 1) % n_slots])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            fn(slots[i % n_slots], slots[(i - 1) % n_slots])
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / reps   # us
+
+    stage_fns = {
+        "S1_bev": lambda s, p: ops.bev_slices(s.points[:, :s.n_points], fe.bev_params, s.maps, s.occ, s.stats, s.ws_bev),
+        "S2_filter": lambda s, p: (ops.integral_image_2d(s.occ, s.ii, s.ws_ii),
+                                   ops.anchor_filter_2d(fe.anchors, s.ii, fe.nx, fe.nz, fe.min_x, fe.min_z,
+                                                        c.voxel_size, c.density_threshold, keep=s.keep),
+                                   ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact)),
+        "S3_rpn_crops": lambda s, p: (ops.crop_and_resize(s.bev_1ch, s.k_bev_boxes, None, c.rpn_crop, 0.0, out=s.rpn_bev_crops, n_dev=s.n_kept),
+                                      ops.crop_and_resize(s.img_1ch, s.k_img_boxes, None, c.rpn_crop, 0.0, out=s.rpn_img_crops, n_dev=s.n_kept)),
+        "S5_rpn_nms": lambda s, p: ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx,
+                                           n_keep=s.n_top, workspace=s.ws_nms_rpn, n_dev=s.n_kept, max_windows=c.nms_max_windows),
+        "S4_correlation": lambda s, p: ops.correlation(p.bev_feat, s.bev_feat, 1, c.corr_max_displacement, 1,
+                                                       c.corr_stride_2, c.corr_padding, out=s.corr),
+        "S3_avod_crops": lambda s, p: (ops.crop_and_resize(s.bev_feat, s.prop_bev_boxes, None, c.avod_crop, 0.0, out=s.bev_rois, n_dev=s.n_top),
+                                       ops.crop_and_resize(s.img_feat, s.prop_img_boxes, None, c.avod_crop, 0.0, out=s.img_rois, n_dev=s.n_top),
+                                       ops.crop_and_resize(s.corr, s.prop_bev_boxes, None, c.avod_crop, 0.0, out=s.corr_rois, n_dev=s.n_top)),
+        "S5_final_nms": lambda s, p: ops.nms(s.prop_bev_boxes, s.final_scores, c.avod_nms_size, c.avod_nms_iou, keep=s.final_idx,
+                                             n_keep=s.n_final, workspace=s.ws_nms_final, n_dev=s.n_top),
+    }
+    stage_us = {k: time_stage(f) for k, f in stage_fns.items()}
+    n_kept = int(slots[0].n_kept.item())
+    n_top = int(slots[0].n_top[0].item())
+    abytes = fe.algorithmic_bytes(n_points, n_kept, n_top)
+    peak, peak_src = measured_peak()
+    corr_us = stage_us["S4_correlation"]            # one launch of corr_tile_k1 per call
+    achieved = abytes["S4"] / (corr_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": "corr_tile_k1<2> (S4 correlation, %.0f%% of the step's "
+                                          "algorithmic bytes)" % (100.0 * abytes["S4"] / abytes["total"]),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": abytes["S4"],
+                "frame": {"algorithmic_bytes": abytes["total"],
+                          "achieved": abytes["total"] * fps / world / 1e9,
+                          "frac": abytes["total"] * fps / world / 1e9 / peak},
+                "stage_us": stage_us, "stage_bytes": abytes}
+
+    # ------------------------------------------------------------------ e2e: host buffers
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream()
+        results_host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
+                         for k, v in s_.result_tensors().items()} for s_ in slots]
+        h2d = sum(v.numel() * v.element_size() for v in host_inputs[0].values())
+        d2h = sum(v.numel() * v.element_size() for v in results_host[0].values())
+        Ke = max(6, min(K, 60))
+        done_ev = [None] * n_slots      # graph that last READ slot j (as current or as prev)
+        copied_ev = [None] * n_slots
+
+        def e2e_loop(n):
+            for i in range(n):
+                j = i % n_slots
+                with torch.cuda.stream(copy_stream):
+                    # slot j was last read by the graph of slot j+1 (as its previous frame), which
+                    # runs after slot j's own graph: wait for it before overwriting the inputs
+                    ev = done_ev[(j + 1) % n_slots]
+                    if ev is not None:
+                        copy_stream.wait_event(ev)
+                    upload(slots[j], host_inputs[j])
+                    copied_ev[j] = torch.cuda.Event()
+                    copied_ev[j].record(copy_stream)
+                main.wait_event(copied_ev[j])
+                graphs[j].replay()
+                for k, v in slots[j].result_tensors().items():
+                    results_host[j][k].copy_(v, non_blocking=True)
+                done_ev[j] = torch.cuda.Event()
+                done_ev[j].record(main)
+
+        e2e_loop(n_slots)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(copy_stream):
+            a.record(copy_stream)
+        e2e_loop(Ke)
+        b.record(main)
+        barrier()
+        ems = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": Ke * world / (float(ems.item()) / 1e3), "unit": "frames/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+               "note": "every slot input (points, BEV/image features, RPN head outputs) copied from "
+                       "pinned host memory each step; detection lists copied back"}
+
+    # ------------------------------------------------------------------ cpu baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        workers = max(1, min(cores, 16))
+        r = cpu_arm(2, 0, workers)
+        cpu = {"value": r["fps"], "unit": "frames/s", "cores": workers, "kind": "port",
+               "sample": "%d frames of the same workload, one per process; S1/S2 NumPy restatement "
+                         "of the reference's NumPy, S3/S4/S5 C restatement (reference S3-S5 are "
+                         "TF/GPU-only)" % r["frames"],
+               "stage_ms_per_frame": r["stage_ms"]}
+
+    if rank == 0:
+        line = {
+            "metric": "front-end frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 binning/predicates, i32 counts)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points": n_points, "anchors": fe.num_anchors,
+                       "anchors_kept": n_kept, "proposals": n_top,
+                       "l2": "inputs %.0f MB/step cycled over %d resident frame slots (> 126 MB L2)"
+                             % (sum(v.numel() * v.element_size() for v in host_inputs[0].values()) / 1e6, n_slots),
+                       "parallelism": "one frame stream per GPU, no data-path collective; one "
+                                      "all_gather of detection lists per shard"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches * K, "launches_per_step": launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -13,6 +13,7 @@ DODT_OK, DODT_EINVAL, DODT_ESHAPE, DODT_ECAPACITY, DODT_ECUDA, DODT_EALIGN = 0, 
 DODT_F32, DODT_F64 = 0, 1
 MAX_SLICES = 15
 MAX_DENSITY_LUT = 64
+NMS_WINDOW = 1536
 BEV_STATS_LEN = 24
 STAT_DENSITY, STAT_OCC, STAT_TOUCHED, STAT_OVERFLOW, STAT_OOB = 16, 17, 18, 19, 20
 
@@ -54,16 +55,21 @@ SIGNATURES = {
     "dodt_anchor_filter_2d": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int32,
                                       c_int32, c_int32, c_double, c_double, c_void_p, c_void_p,
                                       c_void_p]),
+    "dodt_compact_workspace_bytes": (c_size_t, [c_int64]),
+    "dodt_compact_mask": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
+    "dodt_gather_rows": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p,
+                                 c_void_p]),
     "dodt_crop_and_resize": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
-                                     c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p,
-                                     c_void_p]),
+                                     c_void_p, c_int64, c_void_p, c_int32, c_int32, c_float,
+                                     c_void_p, c_void_p]),
     "dodt_correlation_out_shape": (c_int, [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                            c_int32, POINTER(c_int32)]),
     "dodt_correlation": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "dodt_nms_workspace_bytes": (c_size_t, [c_int64]),
-    "dodt_nms": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p,
-                         c_void_p, c_size_t, c_void_p]),
+    "dodt_nms": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_float, c_int32,
+                         c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -61,8 +61,8 @@ __device__ __forceinline__ float bilerp(float tl, float tr, float bl, float br, 
 template <int VEC>
 __global__ void __launch_bounds__(256)
 crop_resize_kernel(const float *__restrict__ image, const float *__restrict__ boxes,
-                   const int *__restrict__ box_ind, long long total, CropGeom g,
-                   float *__restrict__ crops) {
+                   const int *__restrict__ box_ind, const int *__restrict__ n_dev, long long total,
+                   CropGeom g, float *__restrict__ crops) {
   const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (t >= total) return;
   const int cv = g.C / VEC;
@@ -73,7 +73,8 @@ crop_resize_kernel(const float *__restrict__ image, const float *__restrict__ bo
   const int y = static_cast<int>(r % g.crop_h);
   const long long b = r / g.crop_h;
 
-  const int b_in = __ldg(box_ind + b);
+  if (n_dev && b >= __ldg(n_dev)) return;   // box count produced on the device
+  const int b_in = box_ind ? __ldg(box_ind + b) : 0;
   if (b_in < 0 || b_in >= g.batch) return;  // TF leaves such rows untouched
   const float4 box = __ldg(reinterpret_cast<const float4 *>(boxes) + b);  // y1, x1, y2, x2
 
@@ -116,15 +117,15 @@ crop_resize_kernel(const float *__restrict__ image, const float *__restrict__ bo
 
 extern "C" int dodt_crop_and_resize(const float *image, int32_t batch, int32_t height,
                                     int32_t width, int32_t channels, const float *boxes,
-                                    const int32_t *box_ind, int64_t n, int32_t crop_h,
-                                    int32_t crop_w, float extrapolation_value, float *crops,
-                                    dodt_stream_t stream_) {
+                                    const int32_t *box_ind, int64_t n, const int32_t *n_dev,
+                                    int32_t crop_h, int32_t crop_w, float extrapolation_value,
+                                    float *crops, dodt_stream_t stream_) {
   using namespace dodt;
   if (n < 0 || batch <= 0 || height <= 0 || width <= 0 || channels <= 0 || crop_h <= 0 ||
       crop_w <= 0)
     return DODT_EINVAL;
   if (n == 0) return DODT_OK;
-  if (!image || !boxes || !box_ind || !crops) return DODT_EINVAL;
+  if (!image || !boxes || !crops) return DODT_EINVAL;
   if (reinterpret_cast<uintptr_t>(boxes) % 16 != 0) return DODT_EALIGN;
   cudaStream_t stream = as_stream(stream_);
   CropGeom g{batch, height, width, channels, crop_h, crop_w, extrapolation_value};
@@ -134,9 +135,9 @@ extern "C" int dodt_crop_and_resize(const float *image, int32_t batch, int32_t h
   const long long blocks = (total + 255) / 256;
   if (blocks > 0x7FFFFFFFll) return DODT_ECAPACITY;
   if (vec4)
-    crop_resize_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(image, boxes, box_ind, total, g, crops);
+    crop_resize_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(image, boxes, box_ind, n_dev, total, g, crops);
   else
-    crop_resize_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(image, boxes, box_ind, total, g, crops);
+    crop_resize_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(image, boxes, box_ind, n_dev, total, g, crops);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }

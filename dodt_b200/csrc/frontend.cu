@@ -1,0 +1,145 @@
+// Glue kernels of the frame stream: ordered compaction of the anchor keep-mask and row gathers.
+//
+// In the reference these are NumPy boolean / fancy indexing on the host between the stages
+// (avod/core/models/dt_rpn_model.py:952-958 `anchors[anchor_filter]`, :593-597 tf.gather of the
+// NMS survivors). Keeping them on the device lets the whole front end of a frame run without a
+// host round trip: the kept count stays in device memory and the following stages read it there.
+#include "common.cuh"
+
+namespace dodt {
+namespace {
+
+constexpr int kCompactBlock = 1024;
+constexpr int kItems = 4;                               // mask bytes per thread (one uchar4)
+constexpr int kTile = kCompactBlock * kItems;           // 4096 mask entries per CTA
+
+__global__ void __launch_bounds__(kCompactBlock)
+compact_count(const unsigned char *__restrict__ keep, long long n, int *__restrict__ tile_count) {
+  const long long i0 = static_cast<long long>(blockIdx.x) * kTile + threadIdx.x * kItems;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) c += (i0 + k < n && keep[i0 + k]) ? 1 : 0;
+  // block reduction
+  __shared__ int warp_sum[kCompactBlock / 32];
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = warp_sum[threadIdx.x];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (threadIdx.x == 0) tile_count[blockIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+compact_scatter(const unsigned char *__restrict__ keep, long long n,
+                const int *__restrict__ tile_count, int n_tiles, int *__restrict__ idx,
+                int *__restrict__ count) {
+  __shared__ int warp_sum[kCompactBlock / 32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // base of this tile = sum of the counts of all earlier tiles (n_tiles is a few dozen)
+  int part = 0;
+  for (int t = threadIdx.x; t < static_cast<int>(blockIdx.x); t += kCompactBlock) part += tile_count[t];
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_down_sync(0xffffffffu, part, d);
+  if (lane == 0) warp_sum[warp] = part;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = warp_sum[threadIdx.x];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (threadIdx.x == 0) s_base = v;
+  }
+  __syncthreads();
+  const int base = s_base;
+  __syncthreads();
+
+  const long long i0 = static_cast<long long>(blockIdx.x) * kTile + threadIdx.x * kItems;
+  bool f[kItems];
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    f[k] = i0 + k < n && keep[i0 + k];
+    c += f[k] ? 1 : 0;
+  }
+  // exclusive scan of per-thread counts: warp scan, then scan of warp totals
+  int incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int v = warp_sum[threadIdx.x];
+    int w = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += up;
+    }
+    warp_sum[threadIdx.x] = w - v;  // exclusive
+  }
+  __syncthreads();
+  int pos = base + warp_sum[warp] + incl - c;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k)
+    if (f[k]) idx[pos++] = static_cast<int>(i0 + k);
+  if (blockIdx.x == static_cast<unsigned>(n_tiles - 1) && threadIdx.x == kCompactBlock - 1)
+    *count = pos;  // last thread of the last tile ends at the total
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows(const float *__restrict__ src, int width, const int *__restrict__ idx,
+            const int *__restrict__ count, long long n_max, float *__restrict__ dst) {
+  const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  const long long row = t / width;
+  const int col = static_cast<int>(t % width);
+  if (row >= n_max || row >= __ldg(count)) return;
+  dst[t] = __ldg(src + static_cast<long long>(__ldg(idx + row)) * width + col);
+}
+
+}  // namespace
+}  // namespace dodt
+
+extern "C" {
+
+size_t dodt_compact_workspace_bytes(int64_t n) {
+  if (n < 0) return 0;
+  const size_t tiles = (static_cast<size_t>(n) + dodt::kTile - 1) / dodt::kTile;
+  return (tiles + 1) * sizeof(int32_t);
+}
+
+int dodt_compact_mask(const uint8_t *keep, int64_t n, int32_t *idx, int32_t *count,
+                      void *workspace, size_t workspace_bytes, dodt_stream_t stream_) {
+  using namespace dodt;
+  if (n < 0 || n > 0x7FFFFFFF || !count || (n > 0 && (!keep || !idx))) return DODT_EINVAL;
+  cudaStream_t stream = as_stream(stream_);
+  if (n == 0) {
+    DODT_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int32_t), stream));
+    return DODT_OK;
+  }
+  if (!workspace || workspace_bytes < dodt_compact_workspace_bytes(n)) return DODT_ECAPACITY;
+  const int tiles = ceil_div(n, kTile);
+  int *tile_count = static_cast<int *>(workspace);
+  compact_count<<<tiles, kCompactBlock, 0, stream>>>(keep, n, tile_count);
+  DODT_AFTER_LAUNCH();
+  compact_scatter<<<tiles, kCompactBlock, 0, stream>>>(keep, n, tile_count, tiles, idx, count);
+  DODT_AFTER_LAUNCH();
+  return DODT_OK;
+}
+
+int dodt_gather_rows(const float *src, int32_t width, const int32_t *idx, const int32_t *count,
+                     int64_t n_max, float *dst, dodt_stream_t stream_) {
+  using namespace dodt;
+  if (n_max < 0 || width <= 0 || !count || (n_max > 0 && (!src || !idx || !dst))) return DODT_EINVAL;
+  if (n_max == 0) return DODT_OK;
+  const long long total = static_cast<long long>(n_max) * width;
+  const long long blocks = (total + 255) / 256;
+  if (blocks > 0x7FFFFFFFll) return DODT_ECAPACITY;
+  gather_rows<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream_)>>>(src, width, idx, count, n_max, dst);
+  DODT_AFTER_LAUNCH();
+  return DODT_OK;
+}
+
+}  // extern "C"

@@ -34,7 +34,7 @@
 namespace dodt {
 namespace {
 
-constexpr int kWin = 1536;             // candidates per window
+constexpr int kWin = DODT_NMS_WINDOW;  // candidates per window (1536)
 constexpr int kWords = kWin / 64;      // 24 bitmask words per window
 constexpr int kTriWords = 64 * (kWords * (kWords + 1) / 2);  // triangular suppressor store
 constexpr int kRoundThreads = 256;
@@ -64,18 +64,23 @@ __device__ __forceinline__ bool iou_exceeds(const NmsBox &a, float area_a, const
   return iou > thr;
 }
 
+// sort keys (scores; -inf past the device-side candidate count so those sort last) + iota values
 __global__ void __launch_bounds__(256)
-nms_iota(int *__restrict__ idx, int n) {
+nms_prepare(const float *__restrict__ scores, int n, const int *__restrict__ n_dev,
+            float *__restrict__ keys, int *__restrict__ idx) {
   const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i < n) idx[i] = i;
+  if (i >= n) return;
+  const int n_eff = n_dev ? min(n, __ldg(n_dev)) : n;
+  keys[i] = i < n_eff ? __ldg(scores + i) : -INFINITY;
+  idx[i] = i;
 }
 
 // boxes in score order, corners normalised, plus areas
 __global__ void __launch_bounds__(256)
 nms_gather(const float *__restrict__ boxes, const int *__restrict__ order, int n,
-           NmsBox *__restrict__ sbox, float *__restrict__ sarea) {
+           const int *__restrict__ n_dev, NmsBox *__restrict__ sbox, float *__restrict__ sarea) {
   const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
+  if (i >= (n_dev ? min(n, __ldg(n_dev)) : n)) return;
   const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + __ldg(order + i));
   NmsBox o;
   o.ymin = fminf(b.x, b.z); o.xmin = fminf(b.y, b.w);
@@ -92,7 +97,8 @@ __device__ __forceinline__ int tri_off(int i) {
 
 __global__ void __launch_bounds__(kRoundThreads)
 nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
-          const int *__restrict__ order, int n, int base, int max_out, float thr,
+          const int *__restrict__ order, int n_max, const int *__restrict__ n_dev, int base,
+          int max_out, float thr,
           unsigned long long *__restrict__ sup,      // [kTriWords] suppressor bitmasks
           unsigned *__restrict__ dead,               // [kWin/32] killed by earlier windows
           NmsBox *__restrict__ kbox, float *__restrict__ karea,  // kept boxes so far
@@ -105,7 +111,8 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
   __shared__ int s_last;
 
   if (st->done) return;
-  const int wcount = min(kWin, n - base);          // candidates in this window
+  const int n = n_dev ? min(n_max, __ldg(n_dev)) : n_max;
+  const int wcount = max(0, min(kWin, n - base));  // candidates in this window
   const int nb = (wcount + 63) >> 6;               // 64-blocks in this window
   const int n_prev = st->n_kept;                   // boxes kept by earlier windows
   const int pb = (n_prev + 63) >> 6;
@@ -255,14 +262,17 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
     const int total = min(max_out, n_prev + s_prefix[kWords]);
     st->n_kept = total;
     st->tiles_done = 0u;
-    *n_keep = total;
-    if (total >= max_out || base + wcount >= n) st->done = 1;
+    n_keep[0] = total;
+    if (total >= max_out || base + wcount >= n) {
+      st->done = 1;
+      n_keep[1] = 1;   // selection complete
+    }
     __threadfence();
   }
 }
 
 struct NmsLayout {
-  size_t keys_out, vals_in, vals_out, sbox, sarea, kbox, karea, sup, dead, state, cub, total;
+  size_t keys_in, keys_out, vals_in, vals_out, sbox, sarea, kbox, karea, sup, dead, state, cub, total;
   size_t cub_bytes;
 };
 
@@ -272,6 +282,7 @@ int nms_layout(int64_t n, NmsLayout *L) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
   const size_t nn = static_cast<size_t>(n > 0 ? n : 1);
+  L->keys_in = take(nn * 4);
   L->keys_out = take(nn * 4);
   L->vals_in = take(nn * 4);
   L->vals_out = take(nn * 4);
@@ -310,22 +321,28 @@ size_t dodt_nms_workspace_bytes(int64_t n) {
   return L.total;
 }
 
-int dodt_nms(const float *boxes, const float *scores, int64_t n, int32_t max_out,
-             float iou_threshold, int32_t *keep, int32_t *n_keep, void *workspace,
-             size_t workspace_bytes, dodt_stream_t stream_) {
+int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *n_dev,
+             int32_t max_out, float iou_threshold, int32_t max_windows, int32_t *keep,
+             int32_t *n_keep, void *workspace, size_t workspace_bytes, dodt_stream_t stream_) {
   using namespace dodt;
-  if (n < 0 || n > 0x7FFFFFFF || max_out < 0 || !n_keep || (max_out > 0 && !keep)) return DODT_EINVAL;
+  if (n < 0 || n > 0x7FFFFFFF || max_out < 0 || max_windows < 0 || !n_keep || (max_out > 0 && !keep))
+    return DODT_EINVAL;
   if (n > 0 && (!boxes || !scores)) return DODT_EINVAL;
   if (reinterpret_cast<uintptr_t>(boxes) % 16 != 0) return DODT_EALIGN;
   cudaStream_t stream = as_stream(stream_);
-  DODT_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t), stream));
+  DODT_CUDA_TRY(cudaMemsetAsync(n_keep, 0, 2 * sizeof(int32_t), stream));
   if (max_out > 0) DODT_CUDA_TRY(cudaMemsetAsync(keep, 0xFF, sizeof(int32_t) * max_out, stream));
-  if (n == 0 || max_out == 0) return DODT_OK;
+  if (n == 0 || max_out == 0) {
+    // nothing to select: complete. One byte of 0x01 on the zeroed little-endian int32 is 1.
+    DODT_CUDA_TRY(cudaMemsetAsync(n_keep + 1, 1, 1, stream));
+    return DODT_OK;
+  }
   NmsLayout L;
   nms_layout(n, &L);
   if (!workspace || workspace_bytes < L.total) return DODT_ECAPACITY;
   if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return DODT_EALIGN;
   char *ws = static_cast<char *>(workspace);
+  float *keys_in = reinterpret_cast<float *>(ws + L.keys_in);
   float *keys_out = reinterpret_cast<float *>(ws + L.keys_out);
   int *vals_in = reinterpret_cast<int *>(ws + L.vals_in);
   int *order = reinterpret_cast<int *>(ws + L.vals_out);
@@ -340,13 +357,13 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, int32_t max_out
   const int ni = static_cast<int>(n);
   // dead bits and state start at zero (one memset: they are adjacent up to alignment padding)
   DODT_CUDA_TRY(cudaMemsetAsync(ws + L.dead, 0, (L.state - L.dead) + sizeof(NmsState), stream));
-  nms_iota<<<ceil_div(ni, 256), 256, 0, stream>>>(vals_in, ni);
+  nms_prepare<<<ceil_div(ni, 256), 256, 0, stream>>>(scores, ni, n_dev, keys_in, vals_in);
   DODT_AFTER_LAUNCH();
   size_t cub_bytes = L.cub_bytes;
-  DODT_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(ws + L.cub, cub_bytes, scores, keys_out,
+  DODT_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(ws + L.cub, cub_bytes, keys_in, keys_out,
                                                           vals_in, order, ni, 0, 32, stream));
   count_launch(4);  // CUB's histogram + onesweep passes (library kernels)
-  nms_gather<<<ceil_div(ni, 256), 256, 0, stream>>>(boxes, order, ni, sbox, sarea);
+  nms_gather<<<ceil_div(ni, 256), 256, 0, stream>>>(boxes, order, ni, n_dev, sbox, sarea);
   DODT_AFTER_LAUNCH();
 
   const size_t smem = static_cast<size_t>(kTriWords) * sizeof(unsigned long long);
@@ -356,13 +373,15 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, int32_t max_out
                                        static_cast<int>(smem)));
     attr_set = true;
   }
+  int windows = 0;
   for (int base = 0; base < ni; base += kWin) {
+    if (max_windows > 0 && windows++ >= max_windows) break;
     const int wcount = ni - base < kWin ? ni - base : kWin;
     const int nb = (wcount + 63) / 64;
     const int pb = (max_out + 63) / 64;  // upper bound of kept blocks from earlier windows
     int tiles = nb * (nb + 1) / 2 + (base > 0 ? nb * pb : 0);
     const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
-    nms_round<<<grid, kRoundThreads, smem, stream>>>(sbox, sarea, order, ni, base, max_out,
+    nms_round<<<grid, kRoundThreads, smem, stream>>>(sbox, sarea, order, ni, n_dev, base, max_out,
                                                      iou_threshold, sup, dead, kbox, karea, st,
                                                      keep, n_keep);
     DODT_AFTER_LAUNCH();

@@ -165,9 +165,47 @@ def anchor_filter_2d(anchors, ii, nx, nz, min_x, min_z, voxel_size, density_thre
 # ------------------------------------------------------------------------------------------ S3
 
 
-def crop_and_resize(image, boxes, box_ind, crop_size, extrapolation_value=0.0, out=None):
-    """image [B,H,W,C] f32 NHWC, boxes [n,4] f32, box_ind [n] i32 -> [n, ch, cw, C] f32."""
-    _need_cuda(image, boxes, box_ind, out)
+def compact_mask(keep, idx=None, count=None, workspace=None):
+    """keep [n] u8 -> (idx [n] i32 ascending positions of non-zero entries, count [1] i32), device."""
+    _need_cuda(keep, idx, count, workspace)
+    if keep.dtype == torch.bool:
+        keep = keep.view(torch.uint8)
+    keep = keep.contiguous()
+    n = keep.numel()
+    dev = keep.device
+    if idx is None:
+        idx = torch.empty((n,), dtype=torch.int32, device=dev)
+    if count is None:
+        count = torch.empty((1,), dtype=torch.int32, device=dev)
+    if workspace is None:
+        workspace = torch.empty(max(int(load().dodt_compact_workspace_bytes(n)), 256),
+                                dtype=torch.uint8, device=dev)
+    check(load().dodt_compact_mask(_ptr(keep), n, _ptr(idx), _ptr(count), _ptr(workspace),
+                                   workspace.numel(), _stream()), "dodt_compact_mask")
+    return idx, count
+
+
+def gather_rows(src, idx, count, out=None):
+    """out[i] = src[idx[i]] for i < count[0]; src [m, w] (or [m]) f32, idx [n] i32, count [1] i32."""
+    _need_cuda(src, idx, count, out)
+    src = src.contiguous()
+    width = 1 if src.dim() == 1 else int(src.shape[1])
+    n_max = idx.numel()
+    if out is None:
+        out = torch.empty((n_max,) if src.dim() == 1 else (n_max, width), dtype=torch.float32,
+                          device=src.device)
+    check(load().dodt_gather_rows(_ptr(src), width, _ptr(idx), _ptr(count), n_max, _ptr(out),
+                                  _stream()), "dodt_gather_rows")
+    return out
+
+
+def crop_and_resize(image, boxes, box_ind, crop_size, extrapolation_value=0.0, out=None,
+                    n_dev=None):
+    """image [B,H,W,C] f32 NHWC, boxes [n,4] f32, box_ind [n] i32 (None = all zero) ->
+    [n, ch, cw, C] f32. n_dev: optional device int32 box count (rows past it are left untouched)."""
+    if box_ind is None:
+        return _crop_no_ind(image, boxes, crop_size, extrapolation_value, out, n_dev)
+    _need_cuda(image, boxes, box_ind, out, n_dev)
     if image.dim() != 4:
         raise ValueError("image must be 4-D [batch, height, width, channels]")
     if boxes.dim() != 2 or boxes.shape[1] != 4:
@@ -189,8 +227,22 @@ def crop_and_resize(image, boxes, box_ind, crop_size, extrapolation_value=0.0, o
         out = torch.zeros((n, ch, cw, C), dtype=torch.float32, device=image.device) \
             if n and bool(((box_ind < 0) | (box_ind >= B)).any()) \
             else torch.empty((n, ch, cw, C), dtype=torch.float32, device=image.device)
-    check(load().dodt_crop_and_resize(_ptr(image), B, H, W, C, _ptr(boxes), _ptr(box_ind), n, ch,
-                                      cw, float(extrapolation_value), _ptr(out), _stream()),
+    check(load().dodt_crop_and_resize(_ptr(image), B, H, W, C, _ptr(boxes), _ptr(box_ind), n,
+                                      _ptr(n_dev), ch, cw, float(extrapolation_value), _ptr(out),
+                                      _stream()), "dodt_crop_and_resize")
+    return out
+
+
+def _crop_no_ind(image, boxes, crop_size, extrapolation_value, out, n_dev):
+    """Hot-path form: single image batch semantics (box_ind all zero), preallocated buffers."""
+    _need_cuda(image, boxes, out, n_dev)
+    B, H, W, C = image.shape
+    ch, cw = int(crop_size[0]), int(crop_size[1])
+    n = boxes.shape[0]
+    if out is None:
+        out = torch.empty((n, ch, cw, C), dtype=torch.float32, device=image.device)
+    check(load().dodt_crop_and_resize(_ptr(image), B, H, W, C, _ptr(boxes), None, n, _ptr(n_dev),
+                                      ch, cw, float(extrapolation_value), _ptr(out), _stream()),
           "dodt_crop_and_resize")
     return out
 
@@ -239,10 +291,12 @@ def nms_workspace_bytes(n):
     return int(load().dodt_nms_workspace_bytes(int(n)))
 
 
-def nms(boxes, scores, max_out, iou_threshold, keep=None, n_keep=None, workspace=None):
-    """boxes [n,4] f32, scores [n] f32 -> (keep [max_out] i32 padded with -1, n_keep [1] i32),
-    both on the device (no synchronisation)."""
-    _need_cuda(boxes, scores, keep, n_keep, workspace)
+def nms(boxes, scores, max_out, iou_threshold, keep=None, n_keep=None, workspace=None,
+        n_dev=None, max_windows=0):
+    """boxes [n,4] f32, scores [n] f32 -> (keep [max_out] i32 padded with -1, n_keep [2] i32:
+    number selected, 1 if the selection is complete), both on the device (no synchronisation).
+    n_dev: optional device int32 candidate count; max_windows: see include/dodt_fe.h."""
+    _need_cuda(boxes, scores, keep, n_keep, workspace, n_dev)
     if boxes.dim() != 2 or boxes.shape[1] != 4:
         raise ValueError("boxes must be 2-D [num_boxes, 4]")
     if scores.dim() != 1 or scores.shape[0] != boxes.shape[0]:
@@ -259,9 +313,10 @@ def nms(boxes, scores, max_out, iou_threshold, keep=None, n_keep=None, workspace
     if keep is None:
         keep = torch.empty((max_out,), dtype=torch.int32, device=dev)
     if n_keep is None:
-        n_keep = torch.empty((1,), dtype=torch.int32, device=dev)
+        n_keep = torch.empty((2,), dtype=torch.int32, device=dev)
     if workspace is None:
         workspace = torch.empty(max(nms_workspace_bytes(n), 256), dtype=torch.uint8, device=dev)
-    check(load().dodt_nms(_ptr(boxes), _ptr(scores), n, max_out, float(iou_threshold), _ptr(keep),
-                          _ptr(n_keep), _ptr(workspace), workspace.numel(), _stream()), "dodt_nms")
+    check(load().dodt_nms(_ptr(boxes), _ptr(scores), n, _ptr(n_dev), max_out, float(iou_threshold),
+                          int(max_windows), _ptr(keep), _ptr(n_keep), _ptr(workspace),
+                          workspace.numel(), _stream()), "dodt_nms")
     return keep, n_keep

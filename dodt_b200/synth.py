@@ -81,3 +81,38 @@ def crop_boxes(anchors, image_shape=IMAGE_SHAPE):
     _, img_norm = A.project_to_image_space(anchors, A.KITTI_P2, image_shape)
     return (A.reorder_projected_boxes(bev_norm).astype(np.float32),
             A.reorder_projected_boxes(img_norm).astype(np.float32))
+
+
+_ANCHOR_CACHE = None
+
+
+def anchor_set():
+    """(anchors (N,6) f64, their BEV boxes, their image boxes — both [y1,x1,y2,x2] f32)."""
+    global _ANCHOR_CACHE
+    if _ANCHOR_CACHE is None:
+        a = car_anchors()
+        _, bev_norm = A.project_to_bev(a, BEV_EXTENTS)
+        _, img_norm = A.project_to_image_space(a, A.KITTI_P2, IMAGE_SHAPE)
+        _ANCHOR_CACHE = (a, A.reorder_projected_boxes(bev_norm).astype(np.float32),
+                         A.reorder_projected_boxes(img_norm).astype(np.float32))
+    return _ANCHOR_CACHE
+
+
+def frame_inputs(config, frame, n_points=120000, rpn_nms_size=1024):
+    """Host inputs of one frame slot (dodt_b200.frontend.FrameSlot): synthetic sensor data and
+    synthetic network-head outputs, a pure function of (config, frame)."""
+    a, _, _ = anchor_set()
+    rng = np.random.default_rng(1000 * config + frame + 900000)
+    bev_feat, _ = feature_pair(config, frame)                          # [1,700,800,32]
+    img_feat = np.abs(rng.standard_normal((1,) + tuple(IMAGE_SHAPE) + (32,), dtype=np.float32))
+    regressed, bev_norm, scores = rpn_proposals(config, frame, a)
+    _, img_norm = A.project_to_image_space(regressed, A.KITTI_P2, IMAGE_SHAPE)
+    return dict(
+        points=point_cloud(config, frame, n_points),
+        bev_feat=bev_feat, img_feat=img_feat,
+        bev_1ch=np.ascontiguousarray(bev_feat[..., :1]) * np.float32(0.5),
+        img_1ch=np.ascontiguousarray(img_feat[..., :1]) * np.float32(0.5),
+        rpn_boxes=A.reorder_projected_boxes(bev_norm).astype(np.float32),
+        rpn_img_boxes=A.reorder_projected_boxes(img_norm).astype(np.float32),
+        rpn_scores=scores,
+        final_scores=rng.permutation(np.linspace(0.01, 0.99, rpn_nms_size)).astype(np.float32))

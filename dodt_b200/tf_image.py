@@ -44,6 +44,6 @@ def non_max_suppression(boxes, scores, max_output_size, iou_threshold=0.5, name=
     bx, np_in = _dev(boxes, torch.float32)
     sc, _ = _dev(scores, torch.float32)
     keep, n_keep = ops.nms(bx, sc, int(max_output_size), float(iou_threshold))
-    m = int(n_keep.item())
+    m = int(n_keep[0].item())
     sel = keep[:m]
     return sel.cpu().numpy() if np_in else sel

@@ -62,7 +62,7 @@ enum dodt_dtype { DODT_F32 = 0, DODT_F64 = 1 };
 const char *dodt_strerror(int code);
 const char *dodt_last_cuda_error(void); /* thread-local text of the last CUDA failure */
 int dodt_version(void);
-/* number of kernels this library has launched from the calling thread since load
+/* number of kernels this library has launched in this process since load
  * (memset nodes are not counted); used by bench.py for its "gpu_launches" claim */
 int64_t dodt_launch_count(void);
 
@@ -142,16 +142,28 @@ int dodt_anchor_filter_2d(const void *anchors, int32_t dtype, int64_t n, const i
                           double density_threshold, uint8_t *keep, int32_t *scores,
                           dodt_stream_t stream);
 
+/* Ordered compaction of a keep mask — what `anchors[anchor_filter]` (NumPy boolean indexing,
+ * avod/core/models/dt_rpn_model.py:952-958) does on the host in the reference. idx: out int32 [n]
+ * (first *count entries valid, ascending), count: out int32 [1] on the device. */
+size_t dodt_compact_workspace_bytes(int64_t n);
+int dodt_compact_mask(const uint8_t *keep, int64_t n, int32_t *idx, int32_t *count,
+                      void *workspace, size_t workspace_bytes, dodt_stream_t stream);
+/* dst[i, :] = src[idx[i], :] for i < *count (rows of `width` float32); count is a device pointer */
+int dodt_gather_rows(const float *src, int32_t width, const int32_t *idx, const int32_t *count,
+                     int64_t n_max, float *dst, dodt_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * S3 — tf.image.crop_and_resize (TensorFlow 1.3.0 core/kernels/crop_and_resize_op.cc, bilinear),
  * called at avod/core/models/dt_rpn_model.py:418-428 and dt_avod_model.py:253-273.
  * image [batch,H,W,C] f32 NHWC; boxes [n,4] normalised [y1,x1,y2,x2]; box_ind [n] (rows whose
- * index is outside [0,batch) are left untouched, as TF does); crops out [n,crop_h,crop_w,C].
+ * index is outside [0,batch) are left untouched, as TF does; NULL means all zero);
+ * crops out [n,crop_h,crop_w,C]. n_dev: optional device int32 — only the first min(n, *n_dev)
+ * boxes are processed (a box count produced on the device, e.g. by dodt_compact_mask).
  * ---------------------------------------------------------------------------------------- */
 int dodt_crop_and_resize(const float *image, int32_t batch, int32_t height, int32_t width,
                          int32_t channels, const float *boxes, const int32_t *box_ind, int64_t n,
-                         int32_t crop_h, int32_t crop_w, float extrapolation_value, float *crops,
-                         dodt_stream_t stream);
+                         const int32_t *n_dev, int32_t crop_h, int32_t crop_w,
+                         float extrapolation_value, float *crops, dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * S4 — FlowNet correlation forward. Replaces the TF custom op
@@ -174,11 +186,16 @@ int dodt_correlation(const float *a, const float *b, int32_t batch, int32_t heig
  * boxes [n,4] f32 (any corner order), scores [n] f32; keep: out int32 [max_out] (entries past
  * *n_keep are set to -1); n_keep: out int32 [1] on the device; suppress iff IoU > iou_threshold.
  * Equal scores are ordered by ascending index (TF leaves that order unspecified).
+ * n_dev: optional device int32 — the candidate count is min(n, *n_dev) (entries past it are
+ * ignored). max_windows: 0 = enqueue enough windows for any input; k > 0 = enqueue at most k
+ * windows of DODT_NMS_WINDOW score-sorted candidates (fixed launch count for CUDA graphs); if the
+ * selection is not complete after them n_keep[1] is set to 0, else 1. n_keep: out int32 [2].
  * ---------------------------------------------------------------------------------------- */
+#define DODT_NMS_WINDOW 1536
 size_t dodt_nms_workspace_bytes(int64_t n);
-int dodt_nms(const float *boxes, const float *scores, int64_t n, int32_t max_out,
-             float iou_threshold, int32_t *keep, int32_t *n_keep, void *workspace,
-             size_t workspace_bytes, dodt_stream_t stream);
+int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *n_dev,
+             int32_t max_out, float iou_threshold, int32_t max_windows, int32_t *keep,
+             int32_t *n_keep, void *workspace, size_t workspace_bytes, dodt_stream_t stream);
 
 #ifdef __cplusplus
 }

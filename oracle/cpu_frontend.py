@@ -1,0 +1,79 @@
+"""The whole front end of one frame on the CPU through the oracle — TEST INFRASTRUCTURE ONLY
+(used by bench.py's cpu_baseline / --impl reference legs and by the end-to-end parity test).
+
+S1/S2 run the NumPy restatement of the reference's own NumPy code (or, where the read-only
+checkout exists and use_reference=True, that code itself through oracle/ref_shim.py); S3/S4/S5
+run the C restatement (oracle/c_oracle.c). Same stage order and inputs as
+dodt_b200.frontend.FrontEnd.enqueue.
+"""
+import time
+
+import numpy as np
+
+from dodt_b200 import anchors as A
+from dodt_b200 import synth as s
+
+from . import c_oracle as CO
+from . import np_oracle as O
+
+anchors = s.anchor_set
+frame_inputs = s.frame_inputs
+
+
+def run_frame(inp, prev_bev_feat, rpn_nms=(1024, 0.8), avod_nms=(100, 0.01), timings=None):
+    """All stages of one frame; returns the outputs FrontEnd produces (for parity) ."""
+    a, a_bev, a_img = anchors()
+    t = {}
+
+    def tic():
+        return time.perf_counter()
+
+    t0 = tic()
+    pc = inp["points"].astype(np.float64)
+    bev = O.bev_slices(pc, s.GROUND_PLANE, s.AREA_EXTENTS, s.VOXEL_SIZE, s.HEIGHT_LO, s.HEIGHT_HI,
+                       s.NUM_SLICES)
+    t["S1"] = tic() - t0
+    t0 = tic()
+    occ, vox = O.occupancy_grid(pc, s.GROUND_PLANE, s.AREA_EXTENTS, s.VOXEL_SIZE)
+    keep = O.empty_anchor_filter_2d(a, occ, s.VOXEL_SIZE, vox["min_coord"][[0, 2]], 1)
+    kept = np.flatnonzero(keep)
+    t["S2"] = tic() - t0
+    t0 = tic()
+    zeros = np.zeros(len(kept), dtype=np.int32)
+    rpn_bev_crops = CO.crop_and_resize(inp["bev_1ch"], a_bev[kept], zeros, (3, 3))
+    rpn_img_crops = CO.crop_and_resize(inp["img_1ch"], a_img[kept], zeros, (3, 3))
+    t["S3_rpn"] = tic() - t0
+    t0 = tic()
+    k_boxes, k_scores = inp["rpn_boxes"][kept], inp["rpn_scores"][kept]
+    top = CO.non_max_suppression(k_boxes, k_scores, rpn_nms[0], rpn_nms[1])
+    t["S5_rpn"] = tic() - t0
+    t0 = tic()
+    corr = CO.correlation(prev_bev_feat, inp["bev_feat"], 1, 5, 1, 2, 5)
+    t["S4"] = tic() - t0
+    t0 = tic()
+    prop_bev = k_boxes[top]
+    prop_img = inp["rpn_img_boxes"][kept][top]
+    z = np.zeros(len(top), dtype=np.int32)
+    bev_rois = CO.crop_and_resize(inp["bev_feat"], prop_bev, z, (7, 7))
+    img_rois = CO.crop_and_resize(inp["img_feat"], prop_img, z, (7, 7))
+    corr_rois = CO.crop_and_resize(corr, prop_bev, z, (7, 7))
+    t["S3_avod"] = tic() - t0
+    t0 = tic()
+    final = CO.non_max_suppression(prop_bev, inp["final_scores"][:len(top)], avod_nms[0], avod_nms[1])
+    t["S5_avod"] = tic() - t0
+    if timings is not None:
+        timings.update(t)
+    return dict(bev=bev, occ=occ, keep=keep, kept=kept, rpn_bev_crops=rpn_bev_crops,
+                rpn_img_crops=rpn_img_crops, top=top, corr=corr, bev_rois=bev_rois,
+                img_rois=img_rois, corr_rois=corr_rois, final=final)
+
+
+def _worker(args):
+    config, frame = args
+    inp = frame_inputs(config, frame)
+    prev, _ = s.feature_pair(config, frame + 1)
+    t0 = time.perf_counter()
+    timings = {}
+    out = run_frame(inp, prev, timings=timings)
+    dt = time.perf_counter() - t0
+    return dt, timings, int(len(out["top"])), int(len(out["final"]))

@@ -1,0 +1,113 @@
+"""End-to-end parity of the frame-stream runner (dodt_b200.frontend.FrontEnd: all stages of a
+frame enqueued without a host round trip, eager and as a CUDA-graph replay) against the CPU
+oracle's whole-frame restatement (oracle/cpu_frontend.py) on the same synthetic frame."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _upload(slot, inp):
+    for k, dst in slot.input_tensors().items():
+        src = torch.from_numpy(np.ascontiguousarray(inp[k]))
+        if k == "points":
+            dst[:, :src.shape[1]].copy_(src)
+            slot.n_points = src.shape[1]
+        else:
+            dst.copy_(src)
+
+
+def _check(slot, ref):
+    n_kept = int(slot.n_kept.item())
+    assert n_kept == len(ref["kept"])
+    np.testing.assert_array_equal(slot.keep.cpu().numpy().astype(bool), ref["keep"])
+    np.testing.assert_array_equal(slot.kept_idx[:n_kept].cpu().numpy(), ref["kept"])
+    maps = slot.maps.cpu().numpy()
+    for i in range(5):
+        np.testing.assert_array_equal(maps[i], ref["bev"]["height_maps"][i].astype(np.float32))
+    np.testing.assert_array_equal(maps[5], ref["bev"]["density_map"].astype(np.float32))
+    np.testing.assert_array_equal(slot.occ.cpu().numpy(), ref["occ"])
+    np.testing.assert_allclose(slot.rpn_bev_crops[:n_kept].cpu().numpy(), ref["rpn_bev_crops"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(slot.rpn_img_crops[:n_kept].cpu().numpy(), ref["rpn_img_crops"], rtol=1e-5, atol=1e-6)
+    n_top, complete = slot.n_top.cpu().tolist()
+    assert complete == 1 and n_top == len(ref["top"])
+    np.testing.assert_array_equal(slot.top_idx[:n_top].cpu().numpy(), ref["top"])
+    np.testing.assert_allclose(slot.corr.cpu().numpy(), ref["corr"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(slot.bev_rois[:n_top].cpu().numpy(), ref["bev_rois"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(slot.img_rois[:n_top].cpu().numpy(), ref["img_rois"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(slot.corr_rois[:n_top].cpu().numpy(), ref["corr_rois"], rtol=2e-5, atol=1e-6)
+    n_final, complete = slot.n_final.cpu().tolist()
+    assert complete == 1 and n_final == len(ref["final"])
+    np.testing.assert_array_equal(slot.final_idx[:n_final].cpu().numpy(), ref["final"])
+
+
+def test_frontend_frame_eager_and_graph(lib):
+    from dodt_b200 import synth
+    from dodt_b200.frontend import FrontEnd
+    from oracle import cpu_frontend
+    fe = FrontEnd()
+    slots = [fe.new_slot(), fe.new_slot()]
+    inputs = [synth.frame_inputs(2, 40), synth.frame_inputs(2, 41)]
+    for s, inp in zip(slots, inputs):
+        _upload(s, inp)
+    launches = fe.enqueue(slots[1], slots[0])
+    torch.cuda.synchronize()
+    assert launches > 10
+    ref = cpu_frontend.run_frame(inputs[1], inputs[0]["bev_feat"])
+    _check(slots[1], ref)
+    # the same frame as a CUDA-graph replay, after scribbling over the outputs
+    graph, n = fe.capture(slots[1], slots[0])
+    for t in (slots[1].maps, slots[1].corr, slots[1].bev_rois, slots[1].rpn_bev_crops):
+        t.fill_(-1.0)
+    slots[1].top_idx.fill_(-7)
+    graph.replay()
+    torch.cuda.synchronize()
+    _check(slots[1], ref)
+    # replay on new data without re-capturing
+    _upload(slots[1], synth.frame_inputs(2, 42))
+    graph.replay()
+    torch.cuda.synchronize()
+    ref2 = cpu_frontend.run_frame(synth.frame_inputs(2, 42), inputs[0]["bev_feat"])
+    _check(slots[1], ref2)
+
+
+def test_compact_and_gather(lib):
+    from dodt_b200 import ops
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 4095, 4096, 4097, 89600, 300001):
+        keep = (rng.random(n) < 0.37).astype(np.uint8)
+        idx, count = ops.compact_mask(torch.from_numpy(keep).cuda())
+        want = np.flatnonzero(keep)
+        assert int(count.item()) == len(want)
+        np.testing.assert_array_equal(idx[:len(want)].cpu().numpy(), want)
+        src = rng.standard_normal((n, 4)).astype(np.float32)
+        got = ops.gather_rows(torch.from_numpy(src).cuda(), idx, count)
+        np.testing.assert_array_equal(got[:len(want)].cpu().numpy(), src[want])
+    idx, count = ops.compact_mask(torch.zeros(1000, dtype=torch.uint8, device="cuda"))
+    assert int(count.item()) == 0
+
+
+def test_nms_device_count_and_window_cap(lib):
+    """n_dev limits the candidates; max_windows bounds the launches and reports completeness."""
+    from dodt_b200 import ops
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(1)
+    n = 6000
+    c = rng.uniform(0.1, 0.9, (n, 2))
+    boxes = np.concatenate([c - 0.02, c + 0.02], 1).astype(np.float32)
+    scores = rng.permutation(np.linspace(0, 1, n)).astype(np.float32)
+    b, s = torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda()
+    n_dev = torch.tensor([2500], dtype=torch.int32, device="cuda")
+    keep, n_keep = ops.nms(b, s, 4000, 0.3, n_dev=n_dev)
+    want = O.non_max_suppression(boxes[:2500], scores[:2500], 4000, 0.3)
+    assert n_keep.cpu().tolist() == [len(want), 1]
+    np.testing.assert_array_equal(keep[:len(want)].cpu().numpy(), want)
+    keep, n_keep = ops.nms(b, s, 4000, 0.3, max_windows=1)      # 6000 candidates need 4 windows
+    got_n, complete = n_keep.cpu().tolist()
+    assert complete == 0
+    want = O.non_max_suppression(boxes, scores, 4000, 0.3)
+    np.testing.assert_array_equal(keep[:got_n].cpu().numpy(), want[:got_n])
+    keep, n_keep = ops.nms(b, s, 50, 0.3, max_windows=1)        # 50 found inside the first window
+    assert n_keep.cpu().tolist() == [50, 1]
+    np.testing.assert_array_equal(keep.cpu().numpy(), want[:50])
