@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(HERE, "libdodt_fe.so")
 
-SOURCES = ["common.cu", "bev_slices.cu", "anchor_filter.cu", "crop_resize.cu", "correlation.cu",
+SOURCES = ["common.cu", "bev_slices.cu", "anchor_filter.cu", "crop_resize.cu", "correlation.cu", "correlation_tma.cu",
            "nms.cu", "frontend.cu"]
 
 NVCC_FLAGS = [

@@ -27,6 +27,11 @@
 #include "common.cuh"
 
 namespace dodt {
+
+// correlation_tma.cu: TMA-pipelined persistent kernel; returns 1 when it does not apply
+int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, int r, int out_h,
+                    int out_w, int shift, float *out, cudaStream_t stream);
+
 namespace {
 
 struct CorrGeom {
@@ -278,6 +283,11 @@ int dodt_correlation(const float *a, const float *b, int32_t batch, int32_t heig
   // The reference reads the padded temporaries without bounds checks, so parameters that make a
   // displaced patch leave the padded image (pad < max_displacement with large displacements) are
   // undefined there; here such taps are zero.
+  if (g.ks == 1 && g.s1 == 1 && g.s2 == 2 && aligned) {
+    const int done = correlation_tma(a, b, g.batch, g.H, g.W, g.C, g.r, g.out_h, g.out_w,
+                                     g.md - g.pad, out, stream);
+    if (done <= 0) return done;
+  }
   if (g.ks == 1 && g.s1 == 1 && g.s2 == 2 && channels % kCC == 0 && aligned && g.batch <= 65535) {
     int done = 1;
     switch (g.r) {

@@ -1,0 +1,315 @@
+// S4 — correlation, TMA-pipelined persistent kernel for the DODT configuration family
+// (kernel_size 1, stride_1 1, stride_2 2, neighbourhood radius R = max_displacement/2 in {1,2},
+// C % 8 == 0). See correlation.cu for the reference citations and the generic kernels.
+//
+// One persistent CTA per SM (grid = 148), 8 warps; thread 0 doubles as the TMA producer. Work unit = a 16 x 64 tile of output pixels x one chunk of 8 channels:
+//
+//   producer  cp.async.bulk.tensor.4d (TMA) loads the A tile [16 x 66 px x 8 ch] and the B tile
+//             with its 4-pixel halo [24 x 74 px x 8 ch] into one of two 90 KB stages; tile
+//             coordinates may be negative or beyond the image — TMA zero-fills out-of-bounds
+//             elements, which IS the reference's zero padding (PadData + two padded temporaries in
+//             pad.cu.cc / correlation_kernel.cc:69-107 are never materialised). Completion is
+//             signalled on an mbarrier (complete_tx), buffers are handed back through a second
+//             mbarrier, so loads of chunk i+1 overlap the math of chunk i without any CTA-wide
+//             barrier.
+//   consumers each thread owns 4 pixels spaced 2 apart on one row (x0, x0+2, x0+4, x0+6) and all
+//             25 displacements of each: 100 fp32 accumulators live in registers across the four
+//             channel chunks. Per displacement row it reads 8 B-pixel float4s from shared memory
+//             and feeds 20 (pixel, displacement) pairs from them — 10 FMAs per shared-memory
+//             float, which is what keeps the kernel off the shared-memory roofline. Pixel vectors
+//             are 32 bytes with TMA's 32-byte swizzle and the tile pitches are 2 (mod 8) pixels, so
+//             the eight lanes of a quarter-warp always hit eight different 16-byte bank groups.
+//   epilogue  the finished tile (16 x 64 px x 25 floats) is staged through the shared memory of
+//             the stage that was just consumed (plus a 12 KB spare region) and written to HBM
+//             as fully coalesced 128-byte rows; the 100-byte pixel stride of the NHWC(25) output
+//             would otherwise turn every store into 32 partial sectors.
+//
+// Algorithmic HBM bytes per launch: 2*H*W*C*4 read once + H*W*25*4 written once (199.36 MB at
+// 700x800x32); halo re-reads (1.74x of B) are served by the 126 MB L2.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dodt {
+namespace {
+
+constexpr int kTW = 64, kTH = 16, kPX = 4, kCC = 8;
+constexpr int kConsumers = kTW / (2 * kPX) * 2 * kTH;  // 256
+// No dedicated producer warp: ptxas budgets registers for the thread count rounded up to 128, so
+// 288 threads would cap the 100-accumulator consumers at 168 registers (spills). Thread 0 issues
+// the two TMA loads of the NEXT work unit before it starts computing the current one.
+constexpr int kThreads = kConsumers;
+
+template <int R>
+struct TmaCfg {
+  static constexpr int WN = 2 * R + 1;
+  static constexpr int D2 = WN * WN;
+  static constexpr int HALO = 2 * R;                   // stride_2 == 2
+  static constexpr int AW = kTW + 2;                   // pitch = 2 (mod 8)
+  static constexpr int BW = ((kTW + 2 * HALO + 7) / 8) * 8 + 2;
+  static constexpr int BH = kTH + 2 * HALO;
+  static constexpr int A_BYTES = kTH * AW * kCC * 4;
+  static constexpr int B_BYTES = BH * BW * kCC * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_PITCH = kTW * D2 + 2;       // floats; +2 keeps staging stores conflict-free
+  static constexpr int OUT_BYTES = kTH * OUT_PITCH * 4;
+  static constexpr int SPARE = OUT_BYTES > STAGE_BYTES ? OUT_BYTES - STAGE_BYTES : 0;
+  static constexpr int STAGE1_OFF = ((STAGE_BYTES + SPARE + 1023) / 1024) * 1024;
+  static constexpr int BAR_OFF = STAGE1_OFF + STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 64;
+  static_assert(A_BYTES % 1024 == 0, "B tile must stay 1024-byte aligned for the swizzle");
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c0, int c1,
+                                            int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_sync() {   // the 256 compute threads only
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+}
+
+// 32-byte pixel vectors under CU_TENSOR_MAP_SWIZZLE_32B: bit 4 of the byte offset is XORed with
+// bit 7, i.e. the two 16-byte halves of pixel p swap when bit 2 of p is set.
+__device__ __forceinline__ int swz(int pixel, int half) {
+  return pixel * kCC + ((half ^ ((pixel >> 2) & 1)) << 2);
+}
+
+struct CorrTmaGeom {
+  int batch, C, out_h, out_w, shift;  // shift = max_displacement - pad
+  int tiles_x, tiles_y, n_tiles;
+  float inv_unused;
+};
+
+template <int R>
+__global__ void __launch_bounds__(kThreads, 1)
+corr_tma_k1(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const CorrTmaGeom g, float *__restrict__ out) {
+  using Cfg = TmaCfg<R>;
+  constexpr int WN = Cfg::WN, D2 = Cfg::D2, NB = kPX + 2 * R;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_full = smem_base + Cfg::BAR_OFF;        // [2]
+  const uint32_t bar_empty = smem_base + Cfg::BAR_OFF + 16;  // [2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunks = g.C / kCC;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_full + 8, 1);
+    mbar_init(bar_empty, kConsumers / 32);
+    mbar_init(bar_empty + 8, kConsumers / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ TMA issue (thread 0)
+  // work unit `u` = (tile, channel chunk); unit u lives in stage u & 1
+  const int my_tiles = (g.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+  const int n_units = my_tiles * n_chunks;
+  auto issue = [&](int u) {
+    const int tile = blockIdx.x + (u / n_chunks) * gridDim.x;
+    const int ch = u % n_chunks;
+    const int tx = tile % g.tiles_x;
+    const int ty = (tile / g.tiles_x) % g.tiles_y;
+    const int n = tile / (g.tiles_x * g.tiles_y);
+    const int ax = tx * kTW + g.shift, ay = ty * kTH + g.shift;
+    const int stage = u & 1;
+    const uint32_t base = smem_base + (stage ? Cfg::STAGE1_OFF : 0);
+    mbar_wait(bar_empty + 8 * stage, ((u >> 1) & 1) ^ 1);   // consumers released the stage
+    mbar_expect_tx(bar_full + 8 * stage, Cfg::STAGE_BYTES);
+    tma_load_4d(base, &map_a, ch * kCC, ax, ay, n, bar_full + 8 * stage);
+    tma_load_4d(base + Cfg::A_BYTES, &map_b, ch * kCC, ax - Cfg::HALO, ay - Cfg::HALO, n,
+                bar_full + 8 * stage);
+  };
+  if (threadIdx.x == 0 && n_units > 0) issue(0);
+
+  // -------------------------------------------------------------------- consumers
+  // lane bits: [0] parity, [1..2] row & 3, [3..4] group & 3; warps tile 4 (rows) x 2 (x halves)
+  const int row = (warp >> 1) * 4 + ((lane >> 1) & 3);
+  const int x0 = ((warp & 1) * 4 + (lane >> 3)) * (2 * kPX) + (lane & 1);
+  const float sumelems = static_cast<float>(g.C);
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+    float acc[kPX][D2];
+#pragma unroll
+    for (int j = 0; j < kPX; ++j)
+#pragma unroll
+      for (int k = 0; k < D2; ++k) acc[j][k] = 0.0f;
+
+    int stage = 0;
+    for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+      stage = it & 1;
+      if (threadIdx.x == 0 && it + 1 < n_units) issue(it + 1);   // prefetch one unit ahead
+      __syncwarp();
+      const float *sa = reinterpret_cast<const float *>(smem + (stage ? Cfg::STAGE1_OFF : 0));
+      const float *sb = sa + Cfg::A_BYTES / 4;
+      mbar_wait(bar_full + 8 * stage, (it >> 1) & 1);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 va[kPX];
+#pragma unroll
+        for (int j = 0; j < kPX; ++j)
+          va[j] = *reinterpret_cast<const float4 *>(sa + swz(row * Cfg::AW + x0 + 2 * j, half));
+#pragma unroll
+        for (int p = 0; p < WN; ++p) {
+          float4 vb[NB];
+#pragma unroll
+          for (int q = 0; q < NB; ++q)
+            vb[q] = *reinterpret_cast<const float4 *>(
+                sb + swz((row + 2 * p) * Cfg::BW + x0 + 2 * q, half));
+#pragma unroll
+          for (int j = 0; j < kPX; ++j)
+#pragma unroll
+            for (int o = 0; o < WN; ++o) {
+              float s = acc[j][p * WN + o];
+              s = fmaf(va[j].x, vb[j + o].x, s);
+              s = fmaf(va[j].y, vb[j + o].y, s);
+              s = fmaf(va[j].z, vb[j + o].z, s);
+              s = fmaf(va[j].w, vb[j + o].w, s);
+              acc[j][p * WN + o] = s;
+            }
+        }
+      }
+      if (ch + 1 < n_chunks) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+      }
+    }
+
+    // ---- epilogue: stage the tile through the just-consumed stage (+ spare), coalesced stores
+    const int tx = tile % g.tiles_x;
+    const int ty = (tile / g.tiles_x) % g.tiles_y;
+    const int n = tile / (g.tiles_x * g.tiles_y);
+    float *stg = reinterpret_cast<float *>(
+        smem + (stage ? Cfg::STAGE1_OFF + Cfg::STAGE_BYTES - Cfg::OUT_BYTES : 0));
+    consumer_sync();  // every consumer is done reading this stage
+#pragma unroll
+    for (int j = 0; j < kPX; ++j) {
+      float *dst = stg + row * Cfg::OUT_PITCH + (x0 + 2 * j) * D2;
+#pragma unroll
+      for (int k = 0; k < D2; ++k) dst[k] = __fdiv_rn(acc[j][k], sumelems);
+    }
+    consumer_sync();
+    const int valid_rows = min(kTH, g.out_h - ty * kTH);
+    const int valid_floats = min(kTW, g.out_w - tx * kTW) * D2;
+    float *gout = out + ((static_cast<size_t>(n) * g.out_h + ty * kTH) * g.out_w + tx * kTW) * D2;
+    for (int r = warp; r < valid_rows; r += kConsumers / 32) {
+      const float *src = stg + r * Cfg::OUT_PITCH;
+      float *dstrow = gout + static_cast<size_t>(r) * g.out_w * D2;
+      for (int e = lane; e < valid_floats; e += 32) dstrow[e] = src[e];
+    }
+    // generic-proxy accesses to this stage are finished before TMA (async proxy) refills it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+bool make_map(CUtensorMap *map, const float *ptr, int N, int H, int W, int C, int box_w, int box_h) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W),
+                              static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4,
+                                 static_cast<cuuint64_t>(H) * W * C * 4};
+  const cuuint32_t box[4] = {kCC, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(ptr), dims, strides, box,
+             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int R>
+int launch(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w,
+           int shift, float *out, cudaStream_t stream) {
+  using Cfg = TmaCfg<R>;
+  alignas(64) CUtensorMap map_a, map_b;
+  if (!make_map(&map_a, a, N, H, W, C, Cfg::AW, kTH) || !make_map(&map_b, b, N, H, W, C, Cfg::BW, Cfg::BH))
+    return 1;  // not applicable (driver without tensor maps): caller falls back
+  static bool attr_set = false;
+  if (!attr_set) {
+    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_tma_k1<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CorrTmaGeom g;
+  g.batch = N; g.C = C; g.out_h = out_h; g.out_w = out_w; g.shift = shift;
+  g.tiles_x = ceil_div(out_w, kTW);
+  g.tiles_y = ceil_div(out_h, kTH);
+  g.n_tiles = g.tiles_x * g.tiles_y * N;
+  g.inv_unused = 0.f;
+  const int grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
+  corr_tma_k1<R><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(map_a, map_b, g, out);
+  DODT_AFTER_LAUNCH();
+  return DODT_OK;
+}
+
+}  // namespace
+
+// returns DODT_OK if launched, 1 if this path does not apply, DODT_E* on failure
+int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, int r, int out_h,
+                    int out_w, int shift, float *out, cudaStream_t stream) {
+  if (C % kCC != 0 || reinterpret_cast<uintptr_t>(a) % 16 || reinterpret_cast<uintptr_t>(b) % 16)
+    return 1;
+  if (static_cast<long long>(out_h) * out_w < 1024) return 1;  // tiny maps: tiles mostly padding
+  switch (r) {
+    case 1: return launch<1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+    case 2: return launch<2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+    default: return 1;
+  }
+}
+
+}  // namespace dodt
