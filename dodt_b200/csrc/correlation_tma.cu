@@ -27,6 +27,7 @@
 // Algorithmic HBM bytes per launch: 2*H*W*C*4 read once + H*W*25*4 written once (199.36 MB at
 // 700x800x32); halo re-reads (1.74x of B) are served by the 126 MB L2.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -237,6 +238,196 @@ corr_tma_k1(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// cp.async variant (default). ncu on corr_tma_k1 (profiles/r01_corr_tma_ncu.json) shows the
+// tensor-TMA engine delivering only ~8 B/clk/SM for this access pattern: an 8-channel chunk of
+// an NHWC pixel is a 32-byte box row and the engine issues roughly one row request every four
+// cycles, so the consumers sit on the full-barrier. Here the same two-stage pipeline is fed by
+// the 256 compute threads themselves with 16-byte cp.async.cg (LDGSTS, zero-fill for the
+// reference's padding): a thread's 26 copies per work unit differ only by compile-time offsets
+// from one shared-memory and one global base, so the issue cost is ~150 instructions per 900 of
+// math, and one __syncthreads per unit both publishes stage u and frees stage u-1.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
+  const int bytes = valid ? 16 : 0;   // src-size 0: nothing is read, 16 bytes of zeros are written
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes)
+               : "memory");
+}
+
+struct CorrAsyncGeom {
+  int batch, H, W, C, out_h, out_w, shift;
+  int tiles_x, tiles_y, n_tiles;
+  int pow2;       // C is a power of two: divide by multiplying with the exact reciprocal
+  float inv_c;
+};
+
+template <int R>
+__global__ void __launch_bounds__(kConsumers, 1)
+corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const CorrAsyncGeom g,
+              float *__restrict__ out) {
+  using Cfg = TmaCfg<R>;
+  constexpr int WN = Cfg::WN, D2 = Cfg::D2, NB = kPX + 2 * R;
+  constexpr int kBPieces = (kTW + 2 * Cfg::HALO) * 2;   // 16-byte pieces per B tile row
+  constexpr int kAPieces = kTW * 2;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunks = g.C / kCC;
+  const int my_tiles = (g.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+  const int n_units = my_tiles * n_chunks;
+
+  // ---- loader role: thread (ly, lx) copies pieces (row ly + 16 i, piece lx + 16 j)
+  const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
+  const int lhalf = lx & 1, lpx = lx >> 1;
+  const uint32_t a_dst0 = static_cast<uint32_t>(swz(ly * Cfg::AW + lpx, lhalf)) * 4u;
+  const uint32_t b_dst0 = static_cast<uint32_t>(swz(ly * Cfg::BW + lpx, lhalf)) * 4u + Cfg::A_BYTES;
+  const size_t row16 = static_cast<size_t>(16) * g.W * g.C;   // floats per 16 image rows
+
+  auto issue = [&](int u) {
+    const int tile = blockIdx.x + (u / n_chunks) * gridDim.x;
+    const int c0 = (u % n_chunks) * kCC + lhalf * 4;
+    const int tx = tile % g.tiles_x;
+    const int ty = (tile / g.tiles_x) % g.tiles_y;
+    const int n = tile / (g.tiles_x * g.tiles_y);
+    const uint32_t sbase = smem_base + ((u & 1) ? Cfg::STAGE1_OFF : 0);
+    const size_t img = static_cast<size_t>(n) * g.H * g.W * g.C;
+    {  // A tile: 16 rows x 64 px
+      const int gy = ty * kTH + g.shift + ly;
+      const int gx0 = tx * kTW + g.shift + lpx;
+      const bool row_ok = static_cast<unsigned>(gy) < static_cast<unsigned>(g.H);
+      const float *src = a + img + (static_cast<long long>(gy) * g.W + gx0) * g.C + c0;
+#pragma unroll
+      for (int j = 0; j < kAPieces / 16; ++j) {
+        const bool ok = row_ok && static_cast<unsigned>(gx0 + 8 * j) < static_cast<unsigned>(g.W);
+        cp_async16(sbase + a_dst0 + j * 8 * kCC * 4, ok ? src + j * 8 * g.C : a, ok);
+      }
+    }
+    {  // B tile with halo: BH rows x (64 + 2*HALO) px
+      const int gy0 = ty * kTH + g.shift - Cfg::HALO + ly;
+      const int gx0 = tx * kTW + g.shift - Cfg::HALO + lpx;
+      const float *src = b + img + (static_cast<long long>(gy0) * g.W + gx0) * g.C + c0;
+#pragma unroll
+      for (int i = 0; i < (Cfg::BH + 15) / 16; ++i) {
+        const int gy = gy0 + 16 * i;
+        const bool row_ok = (ly + 16 * i < Cfg::BH) &&
+                            static_cast<unsigned>(gy) < static_cast<unsigned>(g.H);
+#pragma unroll
+        for (int j = 0; j < (kBPieces + 15) / 16; ++j) {
+          if (lx + 16 * j < kBPieces && ly + 16 * i < Cfg::BH) {
+            const bool ok = row_ok && static_cast<unsigned>(gx0 + 8 * j) < static_cast<unsigned>(g.W);
+            cp_async16(sbase + b_dst0 + (i * 16 * Cfg::BW + j * 8) * kCC * 4,
+                       ok ? src + i * row16 + j * 8 * g.C : b, ok);
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // ---- compute role (same thread -> pixel mapping as corr_tma_k1)
+  const int row = (warp >> 1) * 4 + ((lane >> 1) & 3);
+  const int x0 = ((warp & 1) * 4 + (lane >> 3)) * (2 * kPX) + (lane & 1);
+  int aoff[kPX], boff[NB];
+#pragma unroll
+  for (int j = 0; j < kPX; ++j) aoff[j] = swz(row * Cfg::AW + x0 + 2 * j, 0);
+#pragma unroll
+  for (int q = 0; q < NB; ++q) boff[q] = swz(row * Cfg::BW + x0 + 2 * q, 0);
+
+  if (n_units > 0) issue(0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+    float acc[kPX][D2];
+#pragma unroll
+    for (int j = 0; j < kPX; ++j)
+#pragma unroll
+      for (int k = 0; k < D2; ++k) acc[j][k] = 0.0f;
+
+    int stage = 0;
+    for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+      stage = it & 1;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();   // unit `it` has landed for everyone; everyone is done with unit it-1
+      if (it + 1 < n_units) issue(it + 1);
+      const float *sa = reinterpret_cast<const float *>(smem + (stage ? Cfg::STAGE1_OFF : 0));
+      const float *sb = sa + Cfg::A_BYTES / 4;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 va[kPX];
+#pragma unroll
+        for (int j = 0; j < kPX; ++j)
+          va[j] = *reinterpret_cast<const float4 *>(sa + (aoff[j] ^ (half << 2)));
+#pragma unroll
+        for (int p = 0; p < WN; ++p) {
+          float4 vb[NB];
+          // rows advance by 2*BW = 148 pixels: bit 2 of the pixel index (the swizzle bit) flips
+          // with every p, the rest of the offset is a compile-time constant
+#pragma unroll
+          for (int q = 0; q < NB; ++q)
+            vb[q] = *reinterpret_cast<const float4 *>(
+                sb + (boff[q] ^ (((p + half) & 1) << 2)) + p * 2 * Cfg::BW * kCC);
+#pragma unroll
+          for (int j = 0; j < kPX; ++j)
+#pragma unroll
+            for (int o = 0; o < WN; ++o) {
+              float s = acc[j][p * WN + o];
+              s = fmaf(va[j].x, vb[j + o].x, s);
+              s = fmaf(va[j].y, vb[j + o].y, s);
+              s = fmaf(va[j].z, vb[j + o].z, s);
+              s = fmaf(va[j].w, vb[j + o].w, s);
+              acc[j][p * WN + o] = s;
+            }
+        }
+      }
+    }
+
+    // ---- epilogue: stage the tile through the just-consumed stage (+ spare), coalesced stores
+    const int tx = tile % g.tiles_x;
+    const int ty = (tile / g.tiles_x) % g.tiles_y;
+    const int n = tile / (g.tiles_x * g.tiles_y);
+    float *stg = reinterpret_cast<float *>(
+        smem + (stage ? Cfg::STAGE1_OFF + Cfg::STAGE_BYTES - Cfg::OUT_BYTES : 0));
+    __syncthreads();  // everyone is done reading this stage
+    if (g.pow2) {
+#pragma unroll
+      for (int j = 0; j < kPX; ++j) {
+        float *dst = stg + row * Cfg::OUT_PITCH + (x0 + 2 * j) * D2;
+#pragma unroll
+        for (int k = 0; k < D2; ++k) dst[k] = __fmul_rn(acc[j][k], g.inv_c);   // exact: 1/2^k
+      }
+    } else {
+      const float sumelems = static_cast<float>(g.C);
+#pragma unroll
+      for (int j = 0; j < kPX; ++j) {
+        float *dst = stg + row * Cfg::OUT_PITCH + (x0 + 2 * j) * D2;
+#pragma unroll
+        for (int k = 0; k < D2; ++k) dst[k] = __fdiv_rn(acc[j][k], sumelems);
+      }
+    }
+    __syncthreads();
+    const int valid_rows = min(kTH, g.out_h - ty * kTH);
+    const int valid_pairs = min(kTW, g.out_w - tx * kTW) * D2 / 2;   // kTW*D2 is even
+    const bool odd_tail = (min(kTW, g.out_w - tx * kTW) * D2) & 1;
+    float *gout = out + ((static_cast<size_t>(n) * g.out_h + ty * kTH) * g.out_w + tx * kTW) * D2;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 8 == 0) && ((g.out_w * D2) % 2 == 0);
+    for (int r = warp; r < valid_rows; r += kConsumers / 32) {
+      const float *src = stg + r * Cfg::OUT_PITCH;
+      float *dstrow = gout + static_cast<size_t>(r) * g.out_w * D2;
+      if (vec_ok) {
+        for (int e = lane; e < valid_pairs; e += 32)
+          reinterpret_cast<float2 *>(dstrow)[e] = reinterpret_cast<const float2 *>(src)[e];
+        if (odd_tail && lane == 0) dstrow[2 * valid_pairs] = src[2 * valid_pairs];
+      } else {
+        const int nf = min(kTW, g.out_w - tx * kTW) * D2;
+        for (int e = lane; e < nf; e += 32) dstrow[e] = src[e];
+      }
+    }
+    // the next iteration's __syncthreads orders these shared-memory reads before the cp.async
+    // writes that refill this stage
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -297,17 +488,53 @@ int launch(const float *a, const float *b, int N, int H, int W, int C, int out_h
   return DODT_OK;
 }
 
+template <int R>
+int launch_async(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w,
+                 int shift, float *out, cudaStream_t stream) {
+  using Cfg = TmaCfg<R>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CorrAsyncGeom g;
+  g.batch = N; g.H = H; g.W = W; g.C = C; g.out_h = out_h; g.out_w = out_w; g.shift = shift;
+  g.tiles_x = ceil_div(out_w, kTW);
+  g.tiles_y = ceil_div(out_h, kTH);
+  g.n_tiles = g.tiles_x * g.tiles_y * N;
+  g.pow2 = (C & (C - 1)) == 0 ? 1 : 0;
+  g.inv_c = 1.0f / static_cast<float>(C);
+  const int grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
+  corr_async_k1<R><<<grid, kConsumers, Cfg::SMEM_BYTES, stream>>>(a, b, g, out);
+  DODT_AFTER_LAUNCH();
+  return DODT_OK;
+}
+
 }  // namespace
 
-// returns DODT_OK if launched, 1 if this path does not apply, DODT_E* on failure
+// returns DODT_OK if launched, 1 if this path does not apply, DODT_E* on failure.
+// impl: 0 = cp.async pipeline (default), 1 = tensor-TMA pipeline (kept for A/B measurements)
 int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, int r, int out_h,
                     int out_w, int shift, float *out, cudaStream_t stream) {
   if (C % kCC != 0 || reinterpret_cast<uintptr_t>(a) % 16 || reinterpret_cast<uintptr_t>(b) % 16)
     return 1;
   if (static_cast<long long>(out_h) * out_w < 1024) return 1;  // tiny maps: tiles mostly padding
+  static int impl = -1;
+  if (impl < 0) {
+    const char *e = getenv("DODT_CORR_IMPL");
+    impl = (e && e[0] == 't') ? 1 : 0;
+  }
+  if (impl == 1) {
+    switch (r) {
+      case 1: return launch<1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      case 2: return launch<2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      default: return 1;
+    }
+  }
   switch (r) {
-    case 1: return launch<1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
-    case 2: return launch<2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+    case 1: return launch_async<1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+    case 2: return launch_async<2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
     default: return 1;
   }
 }
