@@ -249,12 +249,6 @@ corr_tma_k1(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 // from one shared-memory and one global base, so the issue cost is ~150 instructions per 900 of
 // math, and one __syncthreads per unit both publishes stage u and frees stage u-1.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
-  const int bytes = valid ? 16 : 0;   // src-size 0: nothing is read, 16 bytes of zeros are written
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes)
-               : "memory");
-}
-
 struct CorrAsyncGeom {
   int batch, H, W, C, out_h, out_w, shift;
   int tiles_x, tiles_y, n_tiles;
@@ -262,14 +256,21 @@ struct CorrAsyncGeom {
   float inv_c;
 };
 
-template <int R>
-__global__ void __launch_bounds__(kConsumers, 1)
+// PX pixels per thread (spaced 2 apart). PX = 4: 256 threads, 100 accumulators, 10 FMAs per
+// shared-memory float; PX = 2: 512 threads (16 warps), 50 accumulators, 6.7 FMAs per float.
+template <int R, int PX>
+__global__ void __launch_bounds__(kTW / (2 * PX) * 2 * kTH, 1)
 corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const CorrAsyncGeom g,
               float *__restrict__ out) {
   using Cfg = TmaCfg<R>;
-  constexpr int WN = Cfg::WN, D2 = Cfg::D2, NB = kPX + 2 * R;
+  constexpr int WN = Cfg::WN, D2 = Cfg::D2, NB = PX + 2 * R;
+  constexpr int kThr = kTW / (2 * PX) * 2 * kTH;
+  constexpr int kWarps = kThr / 32;
+  constexpr int kWX = kTW / (8 * PX);                   // warps along x
   constexpr int kBPieces = (kTW + 2 * Cfg::HALO) * 2;   // 16-byte pieces per B tile row
   constexpr int kAPieces = kTW * 2;
+  constexpr int kRowThreads = kThr / 16;                // loader rows covered per pass
+  constexpr int kLoadRows = Cfg::BH + kTH;              // B rows then A rows
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -278,14 +279,24 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
                        static_cast<int>(gridDim.x);
   const int n_units = my_tiles * n_chunks;
 
-  // ---- loader role: thread (ly, lx) copies pieces (row ly + 16 i, piece lx + 16 j)
+  // ---- loader role: thread (ly, lx) copies the 16-byte pieces lx, lx+16, ... of load rows
+  // ly, ly+kRowThreads, ...; a load row is a B tile row (first BH rows) or an A tile row. All
+  // copies of a row share one global and one shared base and differ by compile-time offsets;
+  // out-of-image pieces use src-size 0 (zero fill = the reference's padding).
   const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
   const int lhalf = lx & 1, lpx = lx >> 1;
-  const uint32_t a_dst0 = static_cast<uint32_t>(swz(ly * Cfg::AW + lpx, lhalf)) * 4u;
-  const uint32_t b_dst0 = static_cast<uint32_t>(swz(ly * Cfg::BW + lpx, lhalf)) * 4u + Cfg::A_BYTES;
-  const size_t row16 = static_cast<size_t>(16) * g.W * g.C;   // floats per 16 image rows
 
-  auto issue = [&](int u) {
+  // Per-unit loader state: one (global base, shared base, row-valid, first column) per load row.
+  constexpr int kRowsPerThread = (kLoadRows + kRowThreads - 1) / kRowThreads;
+  constexpr int kPiecesPerRow = (kBPieces + 15) / 16;
+  constexpr int kSlices = 2 * WN;                         // one slice per (half, p) math step
+  constexpr int kPiecesPerSlice = (kRowsPerThread * kPiecesPerRow + kSlices - 1) / kSlices;
+  const float *l_src[kRowsPerThread];
+  uint32_t l_dst[kRowsPerThread];
+  int l_gx0[kRowsPerThread];      // first column, or a value that fails every bounds test
+  int l_pieces[kRowsPerThread];
+
+  auto prepare = [&](int u) {
     const int tile = blockIdx.x + (u / n_chunks) * gridDim.x;
     const int c0 = (u % n_chunks) * kCC + lhalf * 4;
     const int tx = tile % g.tiles_x;
@@ -293,54 +304,61 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     const int n = tile / (g.tiles_x * g.tiles_y);
     const uint32_t sbase = smem_base + ((u & 1) ? Cfg::STAGE1_OFF : 0);
     const size_t img = static_cast<size_t>(n) * g.H * g.W * g.C;
-    {  // A tile: 16 rows x 64 px
-      const int gy = ty * kTH + g.shift + ly;
-      const int gx0 = tx * kTW + g.shift + lpx;
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerThread; ++rr) {
+      const int lr = ly + rr * kRowThreads;
+      const bool is_b = lr < Cfg::BH;
+      const int trow = is_b ? lr : lr - Cfg::BH;
+      const int halo = is_b ? Cfg::HALO : 0;
+      const int gy = ty * kTH + g.shift - halo + trow;
+      const int gx0 = tx * kTW + g.shift - halo + lpx;
       const bool row_ok = static_cast<unsigned>(gy) < static_cast<unsigned>(g.H);
-      const float *src = a + img + (static_cast<long long>(gy) * g.W + gx0) * g.C + c0;
-#pragma unroll
-      for (int j = 0; j < kAPieces / 16; ++j) {
-        const bool ok = row_ok && static_cast<unsigned>(gx0 + 8 * j) < static_cast<unsigned>(g.W);
-        cp_async16(sbase + a_dst0 + j * 8 * kCC * 4, ok ? src + j * 8 * g.C : a, ok);
-      }
+      l_src[rr] = (is_b ? b : a) + img + (static_cast<long long>(gy) * g.W + gx0) * g.C + c0;
+      l_dst[rr] = sbase + (is_b ? Cfg::A_BYTES : 0) +
+                  static_cast<uint32_t>(swz(trow * (is_b ? Cfg::BW : Cfg::AW) + lpx, lhalf)) * 4u;
+      l_gx0[rr] = row_ok ? gx0 : (1 << 30);
+      l_pieces[rr] = lr >= kLoadRows ? 0 : (is_b ? kBPieces : kAPieces);
     }
-    {  // B tile with halo: BH rows x (64 + 2*HALO) px
-      const int gy0 = ty * kTH + g.shift - Cfg::HALO + ly;
-      const int gx0 = tx * kTW + g.shift - Cfg::HALO + lpx;
-      const float *src = b + img + (static_cast<long long>(gy0) * g.W + gx0) * g.C + c0;
+  };
+  // copies number slice*kPiecesPerSlice ... of this thread's (row, piece) list
+  auto issue_slice = [&](int slice) {
 #pragma unroll
-      for (int i = 0; i < (Cfg::BH + 15) / 16; ++i) {
-        const int gy = gy0 + 16 * i;
-        const bool row_ok = (ly + 16 * i < Cfg::BH) &&
-                            static_cast<unsigned>(gy) < static_cast<unsigned>(g.H);
-#pragma unroll
-        for (int j = 0; j < (kBPieces + 15) / 16; ++j) {
-          if (lx + 16 * j < kBPieces && ly + 16 * i < Cfg::BH) {
-            const bool ok = row_ok && static_cast<unsigned>(gx0 + 8 * j) < static_cast<unsigned>(g.W);
-            cp_async16(sbase + b_dst0 + (i * 16 * Cfg::BW + j * 8) * kCC * 4,
-                       ok ? src + i * row16 + j * 8 * g.C : b, ok);
-          }
+    for (int k = 0; k < kPiecesPerSlice; ++k) {
+      const int idx = slice * kPiecesPerSlice + k;
+      const int rr = idx / kPiecesPerRow, j = idx % kPiecesPerRow;
+      if (rr < kRowsPerThread) {
+        if (lx + 16 * j < l_pieces[rr]) {
+          const bool ok = static_cast<unsigned>(l_gx0[rr] + 8 * j) < static_cast<unsigned>(g.W);
+          const int bytes = ok ? 16 : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(l_dst[rr] + j * 8 * kCC * 4),
+                       "l"(l_src[rr] + j * 8 * g.C), "r"(bytes)
+                       : "memory");
         }
       }
     }
+  };
+  auto issue = [&](int u) {
+    prepare(u);
+#pragma unroll
+    for (int sl = 0; sl < kSlices; ++sl) issue_slice(sl);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  // ---- compute role (same thread -> pixel mapping as corr_tma_k1)
-  const int row = (warp >> 1) * 4 + ((lane >> 1) & 3);
-  const int x0 = ((warp & 1) * 4 + (lane >> 3)) * (2 * kPX) + (lane & 1);
-  int aoff[kPX], boff[NB];
+  // ---- compute role: lane bits [0] parity, [1..2] row & 3, [3..4] group & 3
+  const int row = (warp / kWX) * 4 + ((lane >> 1) & 3);
+  const int x0 = ((warp % kWX) * 4 + (lane >> 3)) * (2 * PX) + (lane & 1);
+  int aoff[PX], boff[NB];
 #pragma unroll
-  for (int j = 0; j < kPX; ++j) aoff[j] = swz(row * Cfg::AW + x0 + 2 * j, 0);
+  for (int j = 0; j < PX; ++j) aoff[j] = swz(row * Cfg::AW + x0 + 2 * j, 0);
 #pragma unroll
   for (int q = 0; q < NB; ++q) boff[q] = swz(row * Cfg::BW + x0 + 2 * q, 0);
 
   if (n_units > 0) issue(0);
   int it = 0;
   for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-    float acc[kPX][D2];
+    float acc[PX][D2];
 #pragma unroll
-    for (int j = 0; j < kPX; ++j)
+    for (int j = 0; j < PX; ++j)
 #pragma unroll
       for (int k = 0; k < D2; ++k) acc[j][k] = 0.0f;
 
@@ -349,14 +367,15 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
       stage = it & 1;
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();   // unit `it` has landed for everyone; everyone is done with unit it-1
-      if (it + 1 < n_units) issue(it + 1);
+      const bool more = it + 1 < n_units;
+      if (more) prepare(it + 1);
       const float *sa = reinterpret_cast<const float *>(smem + (stage ? Cfg::STAGE1_OFF : 0));
       const float *sb = sa + Cfg::A_BYTES / 4;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        float4 va[kPX];
+        float4 va[PX];
 #pragma unroll
-        for (int j = 0; j < kPX; ++j)
+        for (int j = 0; j < PX; ++j)
           va[j] = *reinterpret_cast<const float4 *>(sa + (aoff[j] ^ (half << 2)));
 #pragma unroll
         for (int p = 0; p < WN; ++p) {
@@ -367,8 +386,11 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
           for (int q = 0; q < NB; ++q)
             vb[q] = *reinterpret_cast<const float4 *>(
                 sb + (boff[q] ^ (((p + half) & 1) << 2)) + p * 2 * Cfg::BW * kCC);
+          // a few of the next unit's cp.async copies ride along with every math step, so the
+          // LSU queue never sees a burst and the copies' latency hides behind the FMAs
+          if (more) issue_slice(half * WN + p);
 #pragma unroll
-          for (int j = 0; j < kPX; ++j)
+          for (int j = 0; j < PX; ++j)
 #pragma unroll
             for (int o = 0; o < WN; ++o) {
               float s = acc[j][p * WN + o];
@@ -380,6 +402,7 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
             }
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
     // ---- epilogue: stage the tile through the just-consumed stage (+ spare), coalesced stores
@@ -391,7 +414,7 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     __syncthreads();  // everyone is done reading this stage
     if (g.pow2) {
 #pragma unroll
-      for (int j = 0; j < kPX; ++j) {
+      for (int j = 0; j < PX; ++j) {
         float *dst = stg + row * Cfg::OUT_PITCH + (x0 + 2 * j) * D2;
 #pragma unroll
         for (int k = 0; k < D2; ++k) dst[k] = __fmul_rn(acc[j][k], g.inv_c);   // exact: 1/2^k
@@ -399,7 +422,7 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     } else {
       const float sumelems = static_cast<float>(g.C);
 #pragma unroll
-      for (int j = 0; j < kPX; ++j) {
+      for (int j = 0; j < PX; ++j) {
         float *dst = stg + row * Cfg::OUT_PITCH + (x0 + 2 * j) * D2;
 #pragma unroll
         for (int k = 0; k < D2; ++k) dst[k] = __fdiv_rn(acc[j][k], sumelems);
@@ -407,20 +430,18 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     }
     __syncthreads();
     const int valid_rows = min(kTH, g.out_h - ty * kTH);
-    const int valid_pairs = min(kTW, g.out_w - tx * kTW) * D2 / 2;   // kTW*D2 is even
-    const bool odd_tail = (min(kTW, g.out_w - tx * kTW) * D2) & 1;
+    const int valid_floats = min(kTW, g.out_w - tx * kTW) * D2;
     float *gout = out + ((static_cast<size_t>(n) * g.out_h + ty * kTH) * g.out_w + tx * kTW) * D2;
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 8 == 0) && ((g.out_w * D2) % 2 == 0);
-    for (int r = warp; r < valid_rows; r += kConsumers / 32) {
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 8 == 0) && ((g.out_w * D2) % 2 == 0) &&
+                        (valid_floats % 2 == 0);
+    for (int r = warp; r < valid_rows; r += kWarps) {
       const float *src = stg + r * Cfg::OUT_PITCH;
       float *dstrow = gout + static_cast<size_t>(r) * g.out_w * D2;
       if (vec_ok) {
-        for (int e = lane; e < valid_pairs; e += 32)
+        for (int e = lane; e < valid_floats / 2; e += 32)
           reinterpret_cast<float2 *>(dstrow)[e] = reinterpret_cast<const float2 *>(src)[e];
-        if (odd_tail && lane == 0) dstrow[2 * valid_pairs] = src[2 * valid_pairs];
       } else {
-        const int nf = min(kTW, g.out_w - tx * kTW) * D2;
-        for (int e = lane; e < nf; e += 32) dstrow[e] = src[e];
+        for (int e = lane; e < valid_floats; e += 32) dstrow[e] = src[e];
       }
     }
     // the next iteration's __syncthreads orders these shared-memory reads before the cp.async
@@ -488,14 +509,15 @@ int launch(const float *a, const float *b, int N, int H, int W, int C, int out_h
   return DODT_OK;
 }
 
-template <int R>
+template <int R, int PX>
 int launch_async(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w,
                  int shift, float *out, cudaStream_t stream) {
   using Cfg = TmaCfg<R>;
+  constexpr int kThr = kTW / (2 * PX) * 2 * kTH;
   static bool attr_set = false;
   if (!attr_set) {
-    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
+    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R, PX>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   CorrAsyncGeom g;
@@ -506,7 +528,7 @@ int launch_async(const float *a, const float *b, int N, int H, int W, int C, int
   g.pow2 = (C & (C - 1)) == 0 ? 1 : 0;
   g.inv_c = 1.0f / static_cast<float>(C);
   const int grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
-  corr_async_k1<R><<<grid, kConsumers, Cfg::SMEM_BYTES, stream>>>(a, b, g, out);
+  corr_async_k1<R, PX><<<grid, kThr, Cfg::SMEM_BYTES, stream>>>(a, b, g, out);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }
@@ -523,7 +545,7 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
   static int impl = -1;
   if (impl < 0) {
     const char *e = getenv("DODT_CORR_IMPL");
-    impl = (e && e[0] == 't') ? 1 : 0;
+    impl = (e && e[0] == 't') ? 1 : ((e && e[0] == '2') ? 2 : 0);
   }
   if (impl == 1) {
     switch (r) {
@@ -532,9 +554,16 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
       default: return 1;
     }
   }
+  if (impl == 2) {   // 16 warps x 2 pixels per thread
+    switch (r) {
+      case 1: return launch_async<1, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      case 2: return launch_async<2, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      default: return 1;
+    }
+  }
   switch (r) {
-    case 1: return launch_async<1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
-    case 2: return launch_async<2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+    case 1: return launch_async<1, 4>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+    case 2: return launch_async<2, 4>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
     default: return 1;
   }
 }
