@@ -36,6 +36,17 @@ class BevParams(Structure):
     ]
 
 
+class GatherSpec(Structure):
+    """struct dodt_gather_spec."""
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("width", c_int32), ("reserved", c_int32)]
+
+
+class CropSpec(Structure):
+    """struct dodt_crop_spec."""
+    _fields_ = [("image", c_void_p), ("boxes", c_void_p), ("crops", c_void_p), ("height", c_int32),
+                ("width", c_int32), ("channels", c_int32), ("reserved", c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/dodt_fe.h declares
 SIGNATURES = {
     "dodt_strerror": (c_char_p, [c_int]),
@@ -60,6 +71,10 @@ SIGNATURES = {
                                   c_void_p]),
     "dodt_gather_rows": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p,
                                  c_void_p]),
+    "dodt_gather_rows_multi": (c_int, [POINTER(GatherSpec), c_int32, c_void_p, c_void_p, c_int64,
+                                       c_void_p]),
+    "dodt_crop_and_resize_multi": (c_int, [POINTER(CropSpec), c_int32, c_int32, c_void_p, c_int64,
+                                           c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "dodt_crop_and_resize": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                      c_void_p, c_int64, c_void_p, c_int32, c_int32, c_float,
                                      c_void_p, c_void_p]),

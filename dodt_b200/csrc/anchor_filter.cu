@@ -15,7 +15,8 @@
 //                    shuffles (uchar4 loads, 128 cells per warp step), row prefixes are staged in
 //                    shared memory as uint16, then the CTA scans the band along x and writes the
 //                    band-local integral image plus the band's column totals.
-//   ii_band_offsets  adds the sum of the column totals of all previous bands (coalesced along z).
+//   ii_band_prefix   exclusive prefix of the band totals along the band axis (one thread per column).
+//   ii_band_offsets  one thread per image element adds its band's offset (coalesced along z).
 //   anchor_box_filter one thread per anchor; anchor rows are staged through shared memory so the
 //                    48-byte rows are read with fully coalesced loads; four L2-resident gathers.
 #include <string.h>
@@ -86,17 +87,29 @@ ii_band_scan(const unsigned char *__restrict__ occ, int nx, int nz, int vec_ok,
   }
 }
 
-__global__ void __launch_bounds__(256)
-ii_band_offsets(int nx, int nz, int *__restrict__ ii, const int *__restrict__ bandsum) {
-  const int z = blockIdx.x * 256 + threadIdx.x;
-  const int band = blockIdx.y + 1;  // band 0 needs no offset
+// in-place exclusive prefix of the band totals along the band axis: bandsum[b][z] becomes the sum
+// of the totals of bands 0..b-1 (one thread per column, loads independent, adds dependent)
+__global__ void __launch_bounds__(128)
+ii_band_prefix(int bands, int nz, int *__restrict__ bandsum) {
+  const int z = blockIdx.x * 128 + threadIdx.x;
   if (z >= nz) return;
-  int off = 0;
-  for (int b = 0; b < band; ++b) off += __ldg(bandsum + static_cast<size_t>(b) * nz + z);
-  if (off == 0) return;
-  const int rows = min(kBand, nx - band * kBand);
-  const int ld = nz + 1;
-  for (int r = 0; r < rows; ++r) ii[static_cast<size_t>(band * kBand + r + 1) * ld + z + 1] += off;
+  int run = 0;
+#pragma unroll 8
+  for (int b = 0; b < bands; ++b) {
+    const int v = bandsum[static_cast<size_t>(b) * nz + z];
+    bandsum[static_cast<size_t>(b) * nz + z] = run;
+    run += v;
+  }
+}
+
+// one thread per integral-image element: add the offset of its band
+__global__ void __launch_bounds__(256)
+ii_band_offsets(int nx, int nz, int *__restrict__ ii, const int *__restrict__ bandoff) {
+  const int z = blockIdx.x * 256 + threadIdx.x;
+  const int x = blockIdx.y;                   // grid row 0..nx-1 <-> image row x+1
+  if (z >= nz || x < kBand) return;           // band 0 needs no offset
+  const int off = __ldg(bandoff + static_cast<size_t>(x / kBand) * nz + z);
+  if (off) ii[static_cast<size_t>(x + 1) * (nz + 1) + z + 1] += off;
 }
 
 template <typename T>
@@ -190,7 +203,9 @@ int dodt_integral_image_2d(const uint8_t *occ, int32_t nx, int32_t nz, int32_t *
   ii_band_scan<<<bands, kBandThreads, smem, stream>>>(occ, nx, nz, vec_ok, ii, bandsum);
   DODT_AFTER_LAUNCH();
   if (bands > 1) {
-    dim3 grid(ceil_div(nz, 256), bands - 1);
+    ii_band_prefix<<<ceil_div(nz, 128), 128, 0, stream>>>(bands, nz, bandsum);
+    DODT_AFTER_LAUNCH();
+    dim3 grid(ceil_div(nz, 256), nx);
     ii_band_offsets<<<grid, 256, 0, stream>>>(nx, nz, ii, bandsum);
     DODT_AFTER_LAUNCH();
   }

@@ -112,8 +112,101 @@ crop_resize_kernel(const float *__restrict__ image, const float *__restrict__ bo
   }
 }
 
+struct CropMulti {
+  const float *image[DODT_MAX_CROP_MAPS];
+  const float *boxes[DODT_MAX_CROP_MAPS];
+  float *crops[DODT_MAX_CROP_MAPS];
+  int H[DODT_MAX_CROP_MAPS], W[DODT_MAX_CROP_MAPS], C[DODT_MAX_CROP_MAPS], vec[DODT_MAX_CROP_MAPS];
+  int batch, crop_h, crop_w;
+  float extrap;
+};
+
+// blockIdx.y selects the map; every map uses its own channel vector width
+__global__ void __launch_bounds__(256)
+crop_resize_multi_kernel(const CropMulti m, const int *__restrict__ box_ind,
+                         const int *__restrict__ n_dev, long long n) {
+  const int s = blockIdx.y;
+  const int vec = m.vec[s];
+  const int C = m.C[s], H = m.H[s], W = m.W[s];
+  const int cv = C / vec;
+  const long long total = n * m.crop_h * m.crop_w * cv;
+  const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (t >= total) return;
+  const int c = static_cast<int>(t % cv) * vec;
+  long long r = t / cv;
+  const int x = static_cast<int>(r % m.crop_w);
+  r /= m.crop_w;
+  const int y = static_cast<int>(r % m.crop_h);
+  const long long b = r / m.crop_h;
+  if (n_dev && b >= __ldg(n_dev)) return;
+  const int b_in = box_ind ? __ldg(box_ind + b) : 0;
+  if (b_in < 0 || b_in >= m.batch) return;
+  const float4 box = __ldg(reinterpret_cast<const float4 *>(m.boxes[s]) + b);
+  float *dst = m.crops[s] + t * vec;
+  int y0, y1i, x0, x1i;
+  float yl, xl;
+  const bool in_y = sample_coord(box.x, box.z, H, m.crop_h, y, &y0, &y1i, &yl);
+  const bool in_x = sample_coord(box.y, box.w, W, m.crop_w, x, &x0, &x1i, &xl);
+  const float *img = m.image[s] + static_cast<size_t>(b_in) * H * W * C + c;
+  if (vec == 4) {
+    float4 o = make_float4(m.extrap, m.extrap, m.extrap, m.extrap);
+    if (in_y && in_x) {
+      const float4 tl = __ldg(reinterpret_cast<const float4 *>(img + (static_cast<size_t>(y0) * W + x0) * C));
+      const float4 tr = __ldg(reinterpret_cast<const float4 *>(img + (static_cast<size_t>(y0) * W + x1i) * C));
+      const float4 bl = __ldg(reinterpret_cast<const float4 *>(img + (static_cast<size_t>(y1i) * W + x0) * C));
+      const float4 br = __ldg(reinterpret_cast<const float4 *>(img + (static_cast<size_t>(y1i) * W + x1i) * C));
+      o.x = bilerp(tl.x, tr.x, bl.x, br.x, xl, yl);
+      o.y = bilerp(tl.y, tr.y, bl.y, br.y, xl, yl);
+      o.z = bilerp(tl.z, tr.z, bl.z, br.z, xl, yl);
+      o.w = bilerp(tl.w, tr.w, bl.w, br.w, xl, yl);
+    }
+    *reinterpret_cast<float4 *>(dst) = o;
+  } else {
+    float o = m.extrap;
+    if (in_y && in_x)
+      o = bilerp(__ldg(img + (static_cast<size_t>(y0) * W + x0) * C),
+                 __ldg(img + (static_cast<size_t>(y0) * W + x1i) * C),
+                 __ldg(img + (static_cast<size_t>(y1i) * W + x0) * C),
+                 __ldg(img + (static_cast<size_t>(y1i) * W + x1i) * C), xl, yl);
+    *dst = o;
+  }
+}
+
 }  // namespace
 }  // namespace dodt
+
+extern "C" int dodt_crop_and_resize_multi(const dodt_crop_spec *specs, int32_t n_specs,
+                                          int32_t batch, const int32_t *box_ind, int64_t n,
+                                          const int32_t *n_dev, int32_t crop_h, int32_t crop_w,
+                                          float extrapolation_value, dodt_stream_t stream_) {
+  using namespace dodt;
+  if (!specs || n_specs <= 0 || n_specs > DODT_MAX_CROP_MAPS || n < 0 || batch <= 0 || crop_h <= 0 ||
+      crop_w <= 0)
+    return DODT_EINVAL;
+  if (n == 0) return DODT_OK;
+  CropMulti m;
+  m.batch = batch; m.crop_h = crop_h; m.crop_w = crop_w; m.extrap = extrapolation_value;
+  long long max_threads = 0;
+  for (int k = 0; k < DODT_MAX_CROP_MAPS; ++k) {
+    const int j = k < n_specs ? k : 0;
+    const dodt_crop_spec &sp = specs[j];
+    if (!sp.image || !sp.boxes || !sp.crops || sp.height <= 0 || sp.width <= 0 || sp.channels <= 0)
+      return DODT_EINVAL;
+    if (reinterpret_cast<uintptr_t>(sp.boxes) % 16 != 0) return DODT_EALIGN;
+    m.image[k] = sp.image; m.boxes[k] = sp.boxes; m.crops[k] = sp.crops;
+    m.H[k] = sp.height; m.W[k] = sp.width; m.C[k] = sp.channels;
+    m.vec[k] = (sp.channels % 4 == 0 && reinterpret_cast<uintptr_t>(sp.image) % 16 == 0 &&
+                reinterpret_cast<uintptr_t>(sp.crops) % 16 == 0) ? 4 : 1;
+    const long long th = static_cast<long long>(n) * crop_h * crop_w * (sp.channels / m.vec[k]);
+    if (k < n_specs && th > max_threads) max_threads = th;
+  }
+  const long long blocks = (max_threads + 255) / 256;
+  if (blocks > 0x7FFFFFFFll) return DODT_ECAPACITY;
+  dim3 grid(static_cast<unsigned>(blocks), n_specs);
+  crop_resize_multi_kernel<<<grid, 256, 0, as_stream(stream_)>>>(m, box_ind, n_dev, n);
+  DODT_AFTER_LAUNCH();
+  return DODT_OK;
+}
 
 extern "C" int dodt_crop_and_resize(const float *image, int32_t batch, int32_t height,
                                     int32_t width, int32_t channels, const float *boxes,

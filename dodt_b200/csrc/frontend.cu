@@ -99,10 +99,65 @@ gather_rows(const float *__restrict__ src, int width, const int *__restrict__ id
   dst[t] = __ldg(src + static_cast<long long>(__ldg(idx + row)) * width + col);
 }
 
+struct GatherMulti {
+  const float *src[DODT_MAX_GATHER];
+  float *dst[DODT_MAX_GATHER];
+  int col_end[DODT_MAX_GATHER];   // exclusive prefix of widths
+  int n_specs;
+  int total_width;
+};
+
+__global__ void __launch_bounds__(256)
+gather_rows_multi(const GatherMulti g, const int *__restrict__ idx, const int *__restrict__ count,
+                  long long n_max) {
+  const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  const long long row = t / g.total_width;
+  int col = static_cast<int>(t % g.total_width);
+  if (row >= n_max || row >= __ldg(count)) return;
+  int s = 0, begin = 0;
+#pragma unroll
+  for (int k = 0; k < DODT_MAX_GATHER; ++k)
+    if (k < g.n_specs && col >= g.col_end[k]) { s = k + 1; begin = g.col_end[k]; }
+  col -= begin;
+  const int width = g.col_end[s] - begin;
+  const long long srow = __ldg(idx + row);
+  g.dst[s][row * width + col] = __ldg(g.src[s] + srow * width + col);
+}
+
 }  // namespace
 }  // namespace dodt
 
 extern "C" {
+
+int dodt_gather_rows_multi(const dodt_gather_spec *specs, int32_t n_specs, const int32_t *idx,
+                           const int32_t *count, int64_t n_max, dodt_stream_t stream_) {
+  using namespace dodt;
+  if (!specs || n_specs <= 0 || n_specs > DODT_MAX_GATHER || n_max < 0 || !count) return DODT_EINVAL;
+  if (n_max == 0) return DODT_OK;
+  if (!idx) return DODT_EINVAL;
+  GatherMulti g;
+  int total = 0;
+  for (int k = 0; k < DODT_MAX_GATHER; ++k) {
+    if (k < n_specs) {
+      if (!specs[k].src || !specs[k].dst || specs[k].width <= 0) return DODT_EINVAL;
+      g.src[k] = specs[k].src;
+      g.dst[k] = specs[k].dst;
+      total += specs[k].width;
+    } else {
+      g.src[k] = nullptr;
+      g.dst[k] = nullptr;
+    }
+    g.col_end[k] = total;
+  }
+  g.n_specs = n_specs;
+  g.total_width = total;
+  const long long threads = static_cast<long long>(n_max) * total;
+  const long long blocks = (threads + 255) / 256;
+  if (blocks > 0x7FFFFFFFll) return DODT_ECAPACITY;
+  gather_rows_multi<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream_)>>>(g, idx, count, n_max);
+  DODT_AFTER_LAUNCH();
+  return DODT_OK;
+}
 
 size_t dodt_compact_workspace_bytes(int64_t n) {
   if (n < 0) return 0;

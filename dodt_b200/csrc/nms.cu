@@ -37,8 +37,9 @@ namespace {
 constexpr int kWin = DODT_NMS_WINDOW;  // candidates per window (1536)
 constexpr int kWords = kWin / 64;      // 24 bitmask words per window
 constexpr int kTriWords = 64 * (kWords * (kWords + 1) / 2);  // triangular suppressor store
-constexpr int kRoundThreads = 256;
+constexpr int kRoundThreads = 1024;
 constexpr int kResolveThreads = kRoundThreads;
+constexpr int kPerThread = (kWin + kResolveThreads - 1) / kResolveThreads;  // candidates per thread
 
 struct NmsState {  // lives in the workspace, zeroed per call
   int n_kept;      // boxes selected so far
@@ -100,13 +101,14 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
           const int *__restrict__ order, int n_max, const int *__restrict__ n_dev, int base,
           int max_out, float thr,
           unsigned long long *__restrict__ sup,      // [kTriWords] suppressor bitmasks
-          unsigned *__restrict__ dead,               // [kWin/32] killed by earlier windows
+          unsigned *__restrict__ dead,               // [2*kWin/32]: killed by earlier windows,
+                                                     // then "has a suppressor in this window"
           NmsBox *__restrict__ kbox, float *__restrict__ karea,  // kept boxes so far
           NmsState *__restrict__ st, int *__restrict__ keep, int *__restrict__ n_keep) {
   extern __shared__ unsigned long long smem_sup[];   // phase 2: [kTriWords]
   __shared__ NmsBox jb[64];
   __shared__ float ja[64];
-  __shared__ unsigned long long s_kept[kWords], s_removed[kWords];
+  __shared__ unsigned long long s_kept[kWords], s_removed[kWords], s_hassup[kWords];
   __shared__ int s_prefix[kWords + 1];
   __shared__ int s_last;
 
@@ -172,6 +174,7 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
           if (m0 | m1) atomicOr(&dead[i >> 5], 1u << (i & 31));
         } else {
           sup[tri_off(i) + bj] = (static_cast<unsigned long long>(m1) << 32) | m0;
+          if (m0 | m1) atomicOr(&dead[kWin / 32 + (i >> 5)], 1u << (i & 31));
         }
       }
     }
@@ -190,7 +193,17 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
 
   // ---------------- phase 2: solve the window ----------------
   const int used_words = 64 * (nb * (nb + 1) / 2);
-  for (int w = threadIdx.x; w < used_words; w += kResolveThreads) smem_sup[w] = __ldcg(sup + w);
+  {
+    int w = threadIdx.x;
+    for (; w + 3 * kResolveThreads < used_words; w += 4 * kResolveThreads) {
+      const unsigned long long v0 = __ldcg(sup + w), v1 = __ldcg(sup + w + kResolveThreads),
+                               v2 = __ldcg(sup + w + 2 * kResolveThreads),
+                               v3 = __ldcg(sup + w + 3 * kResolveThreads);
+      smem_sup[w] = v0; smem_sup[w + kResolveThreads] = v1;
+      smem_sup[w + 2 * kResolveThreads] = v2; smem_sup[w + 3 * kResolveThreads] = v3;
+    }
+    for (; w < used_words; w += kResolveThreads) smem_sup[w] = __ldcg(sup + w);
+  }
   if (threadIdx.x < kWords) {
     const int w = threadIdx.x;
     // bits beyond wcount and candidates killed by earlier windows start as removed
@@ -200,20 +213,27 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
     if (valid <= 0) rem = ~0ull;
     else if (valid < 64) rem |= ~0ull << valid;
     s_removed[w] = rem;
-    s_kept[w] = 0ull;
+    // candidates nobody in this window can suppress are decided at once
+    const unsigned long long hs = (static_cast<unsigned long long>(__ldcg(dead + kWin / 32 + 2 * w + 1)) << 32) |
+                                  __ldcg(dead + kWin / 32 + 2 * w);
+    s_hassup[w] = hs;
+    s_kept[w] = ~rem & ~hs;
   }
   __syncthreads();
 
-  bool undecided[kWin / kResolveThreads];
+  bool undecided[kPerThread];
 #pragma unroll
-  for (int q = 0; q < kWin / kResolveThreads; ++q) undecided[q] = true;
+  for (int q = 0; q < kPerThread; ++q) undecided[q] = true;
   while (true) {
     int pending = 0;
 #pragma unroll
-    for (int q = 0; q < kWin / kResolveThreads; ++q) {
+    for (int q = 0; q < kPerThread; ++q) {
       const int i = q * kResolveThreads + threadIdx.x;
       if (!undecided[q]) continue;
-      if (i >= wcount || ((s_removed[i >> 6] >> (i & 63)) & 1ull)) { undecided[q] = false; continue; }
+      if (i >= wcount || (((s_removed[i >> 6] | ~s_hassup[i >> 6]) >> (i & 63)) & 1ull)) {
+        undecided[q] = false;   // out of range, dead on arrival, or kept because unsuppressable
+        continue;
+      }
       const unsigned long long *row = smem_sup + tri_off(i);
       const int bi = i >> 6;
       bool hit_kept = false, all_removed = true;
@@ -243,7 +263,7 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
   }
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < kWin / kResolveThreads; ++q) {
+  for (int q = 0; q < kPerThread; ++q) {
     const int i = q * kResolveThreads + threadIdx.x;
     if (i >= wcount) continue;
     const unsigned long long kw = s_kept[i >> 6];
@@ -256,7 +276,7 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
     }
   }
   // reset the per-round scratch for the next window
-  for (int w = threadIdx.x; w < kWin / 32; w += kResolveThreads) dead[w] = 0u;
+  for (int w = threadIdx.x; w < 2 * (kWin / 32); w += kResolveThreads) dead[w] = 0u;
   __syncthreads();
   if (threadIdx.x == 0) {
     const int total = min(max_out, n_prev + s_prefix[kWords]);
@@ -291,7 +311,7 @@ int nms_layout(int64_t n, NmsLayout *L) {
   L->kbox = take(nn * sizeof(NmsBox));
   L->karea = take(nn * 4);
   L->sup = take(static_cast<size_t>(kTriWords) * 8);
-  L->dead = take(kWin / 32 * 4);
+  L->dead = take(2 * (kWin / 32) * 4);
   L->state = take(sizeof(NmsState));
   size_t cub_bytes = 0;
   cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(

@@ -48,7 +48,7 @@ class FrontEndConfig:
     corr_max_displacement: int = 5
     corr_padding: int = 5
     corr_stride_2: int = 2
-    nms_max_windows: int = 8                        # launches reserved for the RPN NMS in a graph
+    nms_max_windows: int = 4                        # launches reserved for the RPN NMS in a graph
 
 
 class FrameSlot:
@@ -164,30 +164,27 @@ class FrontEnd:
         ops.anchor_filter_2d(self.anchors, s.ii, self.nx, self.nz, self.min_x, self.min_z,
                              c.voxel_size, c.density_threshold, keep=s.keep)
         ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact)
-        ops.gather_rows(self.anchor_bev_boxes, s.kept_idx, s.n_kept, s.k_bev_boxes)
-        ops.gather_rows(self.anchor_img_boxes, s.kept_idx, s.n_kept, s.k_img_boxes)
-        ops.gather_rows(s.rpn_boxes, s.kept_idx, s.n_kept, s.k_rpn_boxes)
-        ops.gather_rows(s.rpn_img_boxes, s.kept_idx, s.n_kept, s.k_rpn_img_boxes)
-        ops.gather_rows(s.rpn_scores, s.kept_idx, s.n_kept, s.k_rpn_scores)
+        ops.gather_rows_multi([(self.anchor_bev_boxes, s.k_bev_boxes),
+                               (self.anchor_img_boxes, s.k_img_boxes),
+                               (s.rpn_boxes, s.k_rpn_boxes),
+                               (s.rpn_img_boxes, s.k_rpn_img_boxes),
+                               (s.rpn_scores, s.k_rpn_scores)], s.kept_idx, s.n_kept)
         # S3a
-        ops.crop_and_resize(s.bev_1ch, s.k_bev_boxes, None, c.rpn_crop, 0.0, out=s.rpn_bev_crops,
-                            n_dev=s.n_kept)
-        ops.crop_and_resize(s.img_1ch, s.k_img_boxes, None, c.rpn_crop, 0.0, out=s.rpn_img_crops,
-                            n_dev=s.n_kept)
+        ops.crop_and_resize_multi([(s.bev_1ch, s.k_bev_boxes, s.rpn_bev_crops),
+                                   (s.img_1ch, s.k_img_boxes, s.rpn_img_crops)],
+                                  c.rpn_crop, 0.0, n_dev=s.n_kept)
         # S5a
         ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx,
                 n_keep=s.n_top, workspace=s.ws_nms_rpn, n_dev=s.n_kept,
                 max_windows=c.nms_max_windows)
-        ops.gather_rows(s.k_rpn_boxes, s.top_idx, s.n_top, s.prop_bev_boxes)
-        ops.gather_rows(s.k_rpn_img_boxes, s.top_idx, s.n_top, s.prop_img_boxes)
+        ops.gather_rows_multi([(s.k_rpn_boxes, s.prop_bev_boxes),
+                               (s.k_rpn_img_boxes, s.prop_img_boxes)], s.top_idx, s.n_top)
         # S3b (the corr crop needs S4)
-        ops.crop_and_resize(s.bev_feat, s.prop_bev_boxes, None, c.avod_crop, 0.0, out=s.bev_rois,
-                            n_dev=s.n_top)
-        ops.crop_and_resize(s.img_feat, s.prop_img_boxes, None, c.avod_crop, 0.0, out=s.img_rois,
-                            n_dev=s.n_top)
         main.wait_stream(self.side_stream)
-        ops.crop_and_resize(s.corr, s.prop_bev_boxes, None, c.avod_crop, 0.0, out=s.corr_rois,
-                            n_dev=s.n_top)
+        ops.crop_and_resize_multi([(s.bev_feat, s.prop_bev_boxes, s.bev_rois),
+                                   (s.img_feat, s.prop_img_boxes, s.img_rois),
+                                   (s.corr, s.prop_bev_boxes, s.corr_rois)],
+                                  c.avod_crop, 0.0, n_dev=s.n_top)
         # S5b
         ops.nms(s.prop_bev_boxes, s.final_scores, c.avod_nms_size, c.avod_nms_iou,
                 keep=s.final_idx, n_keep=s.n_final, workspace=s.ws_nms_final, n_dev=s.n_top)

@@ -199,6 +199,41 @@ def gather_rows(src, idx, count, out=None):
     return out
 
 
+def gather_rows_multi(pairs, idx, count):
+    """One launch for several (src [m, w], dst [n_max, w]) pairs sharing idx / count."""
+    specs = (_lib.GatherSpec * len(pairs))()
+    for k, (src, dst) in enumerate(pairs):
+        _need_cuda(src, dst)
+        if not src.is_contiguous() or not dst.is_contiguous():
+            raise ValueError("gather_rows_multi needs contiguous tensors")
+        specs[k].src = src.data_ptr()
+        specs[k].dst = dst.data_ptr()
+        specs[k].width = 1 if src.dim() == 1 else int(src.shape[1])
+    check(load().dodt_gather_rows_multi(specs, len(pairs), _ptr(idx), _ptr(count), idx.numel(),
+                                        _stream()), "dodt_gather_rows_multi")
+
+
+def crop_and_resize_multi(triples, crop_size, extrapolation_value=0.0, n_dev=None, box_ind=None):
+    """One launch for several (image [B,H,W,C], boxes [n,4], out [n,ch,cw,C]) triples that share
+    the box count, box_ind (None = zeros) and crop size."""
+    specs = (_lib.CropSpec * len(triples))()
+    n = batch = None
+    for k, (image, boxes, out) in enumerate(triples):
+        _need_cuda(image, boxes, out)
+        B, H, W, C = image.shape
+        if n is None:
+            n, batch = boxes.shape[0], B
+        if boxes.shape[0] != n or B != batch or not (image.is_contiguous() and boxes.is_contiguous()
+                                                      and out.is_contiguous()):
+            raise ValueError("crop_and_resize_multi: inconsistent or non-contiguous inputs")
+        specs[k].image, specs[k].boxes, specs[k].crops = image.data_ptr(), boxes.data_ptr(), out.data_ptr()
+        specs[k].height, specs[k].width, specs[k].channels = H, W, C
+    check(load().dodt_crop_and_resize_multi(specs, len(triples), batch, _ptr(box_ind), n,
+                                            _ptr(n_dev), int(crop_size[0]), int(crop_size[1]),
+                                            float(extrapolation_value), _stream()),
+          "dodt_crop_and_resize_multi")
+
+
 def crop_and_resize(image, boxes, box_ind, crop_size, extrapolation_value=0.0, out=None,
                     n_dev=None):
     """image [B,H,W,C] f32 NHWC, boxes [n,4] f32, box_ind [n] i32 (None = all zero) ->

@@ -151,6 +151,17 @@ int dodt_compact_mask(const uint8_t *keep, int64_t n, int32_t *idx, int32_t *cou
 /* dst[i, :] = src[idx[i], :] for i < *count (rows of `width` float32); count is a device pointer */
 int dodt_gather_rows(const float *src, int32_t width, const int32_t *idx, const int32_t *count,
                      int64_t n_max, float *dst, dodt_stream_t stream);
+/* the same for up to DODT_MAX_GATHER arrays in ONE launch (specs is a host array of device ptrs) */
+#define DODT_MAX_GATHER 8
+typedef struct dodt_gather_spec {
+  const float *src; /* [m, width] */
+  float *dst;       /* [n_max, width] */
+  int32_t width;
+  int32_t reserved;
+} dodt_gather_spec;
+int dodt_gather_rows_multi(const dodt_gather_spec *specs /* host */, int32_t n_specs,
+                           const int32_t *idx, const int32_t *count, int64_t n_max,
+                           dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * S3 — tf.image.crop_and_resize (TensorFlow 1.3.0 core/kernels/crop_and_resize_op.cc, bilinear),
@@ -164,6 +175,22 @@ int dodt_crop_and_resize(const float *image, int32_t batch, int32_t height, int3
                          int32_t channels, const float *boxes, const int32_t *box_ind, int64_t n,
                          const int32_t *n_dev, int32_t crop_h, int32_t crop_w,
                          float extrapolation_value, float *crops, dodt_stream_t stream);
+
+/* Several feature maps cropped with per-map boxes in ONE launch (the reference issues one
+ * tf.image.crop_and_resize per map: BEV + image at dt_rpn_model.py:418-428, BEV + image + corr at
+ * dt_avod_model.py:253-273). All maps share batch, box_ind (NULL = zeros), n, n_dev, crop size. */
+#define DODT_MAX_CROP_MAPS 4
+typedef struct dodt_crop_spec {
+  const float *image; /* [batch, height, width, channels] */
+  const float *boxes; /* [n, 4] */
+  float *crops;       /* [n, crop_h, crop_w, channels] */
+  int32_t height, width, channels;
+  int32_t reserved;
+} dodt_crop_spec;
+int dodt_crop_and_resize_multi(const dodt_crop_spec *specs /* host */, int32_t n_specs,
+                               int32_t batch, const int32_t *box_ind, int64_t n,
+                               const int32_t *n_dev, int32_t crop_h, int32_t crop_w,
+                               float extrapolation_value, dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * S4 — FlowNet correlation forward. Replaces the TF custom op
