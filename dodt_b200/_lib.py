@@ -83,6 +83,7 @@ SIGNATURES = {
     "dodt_correlation": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "dodt_nms_workspace_bytes": (c_size_t, [c_int64]),
+    "dodt_nms_state_offset": (c_size_t, [c_int64]),
     "dodt_nms": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_float, c_int32,
                          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }

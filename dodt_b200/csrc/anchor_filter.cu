@@ -87,18 +87,24 @@ ii_band_scan(const unsigned char *__restrict__ occ, int nx, int nz, int vec_ok,
   }
 }
 
-// in-place exclusive prefix of the band totals along the band axis: bandsum[b][z] becomes the sum
-// of the totals of bands 0..b-1 (one thread per column, loads independent, adds dependent)
-__global__ void __launch_bounds__(128)
-ii_band_prefix(int bands, int nz, int *__restrict__ bandsum) {
-  const int z = blockIdx.x * 128 + threadIdx.x;
+// exclusive prefix of the band totals along the band axis: bandoff[b][z] = sum of bandsum[0..b-1][z].
+// One thread per column; separate in/out arrays so that the loads of a chunk are all in flight
+// before the dependent adds start.
+__global__ void __launch_bounds__(64)
+ii_band_prefix(int bands, int nz, const int *__restrict__ bandsum, int *__restrict__ bandoff) {
+  const int z = blockIdx.x * 64 + threadIdx.x;
   if (z >= nz) return;
   int run = 0;
-#pragma unroll 8
-  for (int b = 0; b < bands; ++b) {
-    const int v = bandsum[static_cast<size_t>(b) * nz + z];
-    bandsum[static_cast<size_t>(b) * nz + z] = run;
-    run += v;
+  for (int b0 = 0; b0 < bands; b0 += 16) {
+    int v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      v[k] = b0 + k < bands ? __ldg(bandsum + static_cast<size_t>(b0 + k) * nz + z) : 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (b0 + k < bands) bandoff[static_cast<size_t>(b0 + k) * nz + z] = run;
+      run += v[k];
+    }
   }
 }
 
@@ -181,7 +187,7 @@ extern "C" {
 size_t dodt_integral_workspace_bytes(int32_t nx, int32_t nz) {
   if (nx <= 0 || nz <= 0) return 0;
   const size_t bands = (static_cast<size_t>(nx) + dodt::kBand - 1) / dodt::kBand;
-  return bands * nz * sizeof(int32_t);
+  return 2 * bands * nz * sizeof(int32_t);  // band totals + their exclusive prefix
 }
 
 int dodt_integral_image_2d(const uint8_t *occ, int32_t nx, int32_t nz, int32_t *ii,
@@ -203,10 +209,11 @@ int dodt_integral_image_2d(const uint8_t *occ, int32_t nx, int32_t nz, int32_t *
   ii_band_scan<<<bands, kBandThreads, smem, stream>>>(occ, nx, nz, vec_ok, ii, bandsum);
   DODT_AFTER_LAUNCH();
   if (bands > 1) {
-    ii_band_prefix<<<ceil_div(nz, 128), 128, 0, stream>>>(bands, nz, bandsum);
+    int *bandoff = bandsum + static_cast<size_t>(bands) * nz;
+    ii_band_prefix<<<ceil_div(nz, 64), 64, 0, stream>>>(bands, nz, bandsum, bandoff);
     DODT_AFTER_LAUNCH();
     dim3 grid(ceil_div(nz, 256), nx);
-    ii_band_offsets<<<grid, 256, 0, stream>>>(nx, nz, ii, bandsum);
+    ii_band_offsets<<<grid, 256, 0, stream>>>(nx, nz, ii, bandoff);
     DODT_AFTER_LAUNCH();
   }
   return DODT_OK;

@@ -45,8 +45,15 @@ struct NmsState {  // lives in the workspace, zeroed per call
   int n_kept;      // boxes selected so far
   int done;        // selection complete
   unsigned tiles_done;  // CTA completion ticket of the current round
-  int pad;
+  int sweeps;           // relaxation sweeps of the last solved window (diagnostic)
+  unsigned long long t_ns[6];  // globaltimer at phase boundaries of the last solved window (diagnostic)
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct NmsBox {
   float ymin, xmin, ymax, xmax;
@@ -90,11 +97,61 @@ nms_gather(const float *__restrict__ boxes, const int *__restrict__ order, int n
   sarea[i] = __fmul_rn(__fsub_rn(o.ymax, o.ymin), __fsub_rn(o.xmax, o.xmin));
 }
 
-// word offset of candidate i's suppressor words (words 0 .. i/64) in the triangular store
-__device__ __forceinline__ int tri_off(int i) {
-  const int bi = i >> 6;
-  return 64 * (bi * (bi + 1) / 2) + (i & 63) * (bi + 1);
+// Candidate sets of up to kSmallSort boxes (the final NMS: 1024 proposals) are ordered by one CTA
+// with a bitonic network in shared memory on the 64-bit key (descending score, ascending index)
+// and written out already gathered — one launch instead of prepare + radix sort + gather.
+constexpr int kSmallSort = 4096;
+
+__device__ __forceinline__ unsigned desc_key(float f) {
+  const unsigned u = __float_as_uint(f);
+  const unsigned asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending float order
+  return ~asc;                                                       // smaller = higher score
 }
+
+__global__ void __launch_bounds__(1024)
+nms_sort_small(const float *__restrict__ boxes, const float *__restrict__ scores, int n,
+               const int *__restrict__ n_dev, int padded, int *__restrict__ order,
+               NmsBox *__restrict__ sbox, float *__restrict__ sarea) {
+  __shared__ unsigned long long key[kSmallSort];
+  const int n_eff = n_dev ? min(n, __ldg(n_dev)) : n;
+  for (int i = threadIdx.x; i < padded; i += 1024)
+    key[i] = i < n_eff ? (static_cast<unsigned long long>(desc_key(__ldg(scores + i))) << 32) | static_cast<unsigned>(i)
+                       : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= padded; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < padded / 2; t += 1024) {
+        // t-th compare-exchange of this stage: lower index i has bit j clear
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const unsigned long long a = key[i], b = key[p];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { key[i] = b; key[p] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n_eff; i += 1024) {
+    const int src = static_cast<int>(key[i] & 0xFFFFFFFFull);
+    order[i] = src;
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + src);
+    NmsBox o;
+    o.ymin = fminf(b.x, b.z); o.xmin = fminf(b.y, b.w);
+    o.ymax = fmaxf(b.x, b.z); o.xmax = fmaxf(b.y, b.w);
+    sbox[i] = o;
+    sarea[i] = __fmul_rn(__fsub_rn(o.ymax, o.ymin), __fsub_rn(o.xmax, o.xmin));
+  }
+}
+
+// Triangular suppressor store: block bi (64 candidates) owns words 0..bi, laid out word-major
+// ([w][64 candidates]) so that the 32 lanes of a warp, which solve 32 consecutive candidates, read
+// 32 consecutive 8-byte words (a candidate-major layout strides by (bi+1)*8 bytes: 32-way bank
+// conflicts at bi = 15).
+__device__ __forceinline__ int tri_base(int i) {
+  const int bi = i >> 6;
+  return 64 * (bi * (bi + 1) / 2) + (i & 63);
+}
+__device__ __forceinline__ int tri_word(int i, int w) { return tri_base(i) + w * 64; }
 
 __global__ void __launch_bounds__(kRoundThreads)
 nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
@@ -113,6 +170,7 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
   __shared__ int s_last;
 
   if (st->done) return;
+  const unsigned long long t_start = global_ns();
   const int n = n_dev ? min(n_max, __ldg(n_dev)) : n_max;
   const int wcount = max(0, min(kWin, n - base));  // candidates in this window
   const int nb = (wcount + 63) >> 6;               // 64-blocks in this window
@@ -173,7 +231,7 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
         if (vs_prev) {
           if (m0 | m1) atomicOr(&dead[i >> 5], 1u << (i & 31));
         } else {
-          sup[tri_off(i) + bj] = (static_cast<unsigned long long>(m1) << 32) | m0;
+          sup[tri_word(i, bj)] = (static_cast<unsigned long long>(m1) << 32) | m0;
           if (m0 | m1) atomicOr(&dead[kWin / 32 + (i >> 5)], 1u << (i & 31));
         }
       }
@@ -190,6 +248,7 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (threadIdx.x == 0) { st->t_ns[0] = t_start; st->t_ns[1] = global_ns(); }
 
   // ---------------- phase 2: solve the window ----------------
   const int used_words = 64 * (nb * (nb + 1) / 2);
@@ -221,41 +280,66 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
   }
   __syncthreads();
 
+  if (threadIdx.x == 0) st->t_ns[2] = global_ns();
   bool undecided[kPerThread];
 #pragma unroll
   for (int q = 0; q < kPerThread; ++q) undecided[q] = true;
+  int sweeps = 0;
+  unsigned nz[kPerThread];
+#pragma unroll
+  for (int q = 0; q < kPerThread; ++q) nz[q] = 0;
   while (true) {
+    ++sweeps;
     int pending = 0;
+    bool now_kept[kPerThread], now_removed[kPerThread];
 #pragma unroll
     for (int q = 0; q < kPerThread; ++q) {
       const int i = q * kResolveThreads + threadIdx.x;
+      now_kept[q] = false;
+      now_removed[q] = false;
       if (!undecided[q]) continue;
       if (i >= wcount || (((s_removed[i >> 6] | ~s_hassup[i >> 6]) >> (i & 63)) & 1ull)) {
         undecided[q] = false;   // out of range, dead on arrival, or kept because unsuppressable
         continue;
       }
-      const unsigned long long *row = smem_sup + tri_off(i);
-      const int bi = i >> 6;
+      const unsigned long long *row = smem_sup + tri_base(i);
+      if (sweeps == 1) {   // remember which of the candidate's words hold any suppressor at all
+        const int bi = i >> 6;
+        unsigned m = 0;
+        for (int w = 0; w <= bi; ++w)
+          if (row[w * 64]) m |= 1u << w;
+        nz[q] = m;
+      }
       bool hit_kept = false, all_removed = true;
-      for (int w = 0; w <= bi; ++w) {
-        const unsigned long long s = row[w];
+      for (unsigned m = nz[q]; m; m &= m - 1) {
+        const int w = __ffs(m) - 1;
+        const unsigned long long s = row[w * 64];
         if (s & s_kept[w]) { hit_kept = true; break; }
         if (s & ~s_removed[w]) all_removed = false;
       }
-      if (hit_kept) {
-        atomicOr(&s_removed[bi], 1ull << (i & 63));
-        undecided[q] = false;
-      } else if (all_removed) {
-        atomicOr(&s_kept[bi], 1ull << (i & 63));
-        undecided[q] = false;
-      } else {
-        pending = 1;
+      now_removed[q] = hit_kept;
+      now_kept[q] = !hit_kept && all_removed;
+      if (hit_kept || all_removed) undecided[q] = false; else pending = 1;
+    }
+    // publish: a warp's 32 candidates of slot q are exactly one 32-bit half of a state word, so
+    // one lane ORs the ballot in — no shared-memory atomics (64-bit ones are CAS loops)
+#pragma unroll
+    for (int q = 0; q < kPerThread; ++q) {
+      const unsigned mk = __ballot_sync(0xffffffffu, now_kept[q]);
+      const unsigned mr = __ballot_sync(0xffffffffu, now_removed[q]);
+      const int i0 = q * kResolveThreads + (threadIdx.x & ~31);
+      if (lane == 0 && i0 < kWin) {
+        unsigned *k32 = reinterpret_cast<unsigned *>(s_kept) + (i0 >> 5);
+        unsigned *r32 = reinterpret_cast<unsigned *>(s_removed) + (i0 >> 5);
+        if (mk) *k32 |= mk;
+        if (mr) *r32 |= mr;
       }
     }
     if (!__syncthreads_or(pending)) break;
   }
 
   // ---------------- emit: kept candidates in score order, cut at max_out ----------------
+  if (threadIdx.x == 0) { st->t_ns[3] = global_ns(); st->sweeps = sweeps; }
   if (threadIdx.x == 0) {
     int run = 0;
     for (int w = 0; w < kWords; ++w) { s_prefix[w] = run; run += __popcll(s_kept[w]); }
@@ -282,6 +366,7 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
     const int total = min(max_out, n_prev + s_prefix[kWords]);
     st->n_kept = total;
     st->tiles_done = 0u;
+    st->t_ns[4] = global_ns();
     n_keep[0] = total;
     if (total >= max_out || base + wcount >= n) {
       st->done = 1;
@@ -334,6 +419,13 @@ int nms_layout(int64_t n, NmsLayout *L) {
 
 extern "C" {
 
+size_t dodt_nms_state_offset(int64_t n) {
+  if (n < 0 || n > 0x7FFFFFFF) return 0;
+  dodt::NmsLayout L;
+  dodt::nms_layout(n, &L);
+  return L.state;
+}
+
 size_t dodt_nms_workspace_bytes(int64_t n) {
   if (n < 0 || n > 0x7FFFFFFF) return 0;
   dodt::NmsLayout L;
@@ -377,14 +469,21 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *
   const int ni = static_cast<int>(n);
   // dead bits and state start at zero (one memset: they are adjacent up to alignment padding)
   DODT_CUDA_TRY(cudaMemsetAsync(ws + L.dead, 0, (L.state - L.dead) + sizeof(NmsState), stream));
-  nms_prepare<<<ceil_div(ni, 256), 256, 0, stream>>>(scores, ni, n_dev, keys_in, vals_in);
-  DODT_AFTER_LAUNCH();
-  size_t cub_bytes = L.cub_bytes;
-  DODT_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(ws + L.cub, cub_bytes, keys_in, keys_out,
-                                                          vals_in, order, ni, 0, 32, stream));
-  count_launch(4);  // CUB's histogram + onesweep passes (library kernels)
-  nms_gather<<<ceil_div(ni, 256), 256, 0, stream>>>(boxes, order, ni, n_dev, sbox, sarea);
-  DODT_AFTER_LAUNCH();
+  if (ni <= kSmallSort) {
+    int padded = 2;
+    while (padded < ni) padded <<= 1;
+    nms_sort_small<<<1, 1024, 0, stream>>>(boxes, scores, ni, n_dev, padded, order, sbox, sarea);
+    DODT_AFTER_LAUNCH();
+  } else {
+    nms_prepare<<<ceil_div(ni, 256), 256, 0, stream>>>(scores, ni, n_dev, keys_in, vals_in);
+    DODT_AFTER_LAUNCH();
+    size_t cub_bytes = L.cub_bytes;
+    DODT_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(ws + L.cub, cub_bytes, keys_in, keys_out,
+                                                            vals_in, order, ni, 0, 32, stream));
+    count_launch(6);  // CUB's histogram, scan and four onesweep passes (library kernels)
+    nms_gather<<<ceil_div(ni, 256), 256, 0, stream>>>(boxes, order, ni, n_dev, sbox, sarea);
+    DODT_AFTER_LAUNCH();
+  }
 
   const size_t smem = static_cast<size_t>(kTriWords) * sizeof(unsigned long long);
   static bool attr_set = false;  // per process; the attribute is a property of the function
@@ -400,7 +499,10 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *
     const int nb = (wcount + 63) / 64;
     const int pb = (max_out + 63) / 64;  // upper bound of kept blocks from earlier windows
     int tiles = nb * (nb + 1) / 2 + (base > 0 ? nb * pb : 0);
-    const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
+    // the first window gets the whole GPU; later windows usually find the selection complete and
+    // exit, so they are launched narrower (cheaper no-op, still 10 tiles per CTA when they run)
+    const int cap = base == 0 ? 2 * kNumSMs : kNumSMs / 2;
+    const int grid = tiles < cap ? tiles : cap;
     nms_round<<<grid, kRoundThreads, smem, stream>>>(sbox, sarea, order, ni, n_dev, base, max_out,
                                                      iou_threshold, sup, dead, kbox, karea, st,
                                                      keep, n_keep);

@@ -220,6 +220,10 @@ int dodt_correlation(const float *a, const float *b, int32_t batch, int32_t heig
  * ---------------------------------------------------------------------------------------- */
 #define DODT_NMS_WINDOW 1536
 size_t dodt_nms_workspace_bytes(int64_t n);
+/* byte offset, inside the workspace, of the diagnostic block of the last solved window:
+ * int32 {n_kept, done, ticket, sweeps} then uint64 globaltimer[6] {kernel start, IoU tiles done,
+ * masks in shared memory, recurrence solved, emitted, -} */
+size_t dodt_nms_state_offset(int64_t n);
 int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *n_dev,
              int32_t max_out, float iou_threshold, int32_t max_windows, int32_t *keep,
              int32_t *n_keep, void *workspace, size_t workspace_bytes, dodt_stream_t stream);

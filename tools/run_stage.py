@@ -38,6 +38,9 @@ for _ in range(reps):
     elif what == "nms":
         ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx, n_keep=s.n_top,
                 workspace=s.ws_nms_rpn, n_dev=s.n_kept, max_windows=c.nms_max_windows)
+    elif what == "final":
+        ops.nms(s.prop_bev_boxes, s.final_scores, c.avod_nms_size, c.avod_nms_iou, keep=s.final_idx,
+                n_keep=s.n_final, workspace=s.ws_nms_final, n_dev=s.n_top)
     elif what == "crops":
         ops.crop_and_resize(s.bev_feat, s.prop_bev_boxes, None, c.avod_crop, 0.0, out=s.bev_rois, n_dev=s.n_top)
         ops.crop_and_resize(s.bev_1ch, s.k_bev_boxes, None, c.rpn_crop, 0.0, out=s.rpn_bev_crops, n_dev=s.n_kept)
