@@ -254,6 +254,7 @@ int dodt_correlation_out_shape(int32_t height, int32_t width, int32_t kernel_siz
   if (!out_hwc || height <= 0 || width <= 0 || kernel_size <= 0 || max_displacement < 0 ||
       stride_1 <= 0 || stride_2 <= 0 || pad < 0)
     return DODT_EINVAL;
+  if (kernel_size % 2 == 0) return DODT_EINVAL;  // correlation_kernel.cc:23 "kernel_size must be odd"
   // correlation_kernel.cc:39-57 (float ceil, as the reference computes it)
   const int kernel_radius = (kernel_size - 1) / 2;
   const int border = max_displacement + kernel_radius;
