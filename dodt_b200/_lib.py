@@ -14,6 +14,7 @@ DODT_F32, DODT_F64 = 0, 1
 MAX_SLICES = 15
 MAX_DENSITY_LUT = 64
 NMS_WINDOW = 1536
+NMS_CHUNK_WINDOWS = 2
 BEV_STATS_LEN = 24
 STAT_DENSITY, STAT_OCC, STAT_TOUCHED, STAT_OVERFLOW, STAT_OOB = 16, 17, 18, 19, 20
 
@@ -84,7 +85,7 @@ SIGNATURES = {
                                  c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "dodt_nms_workspace_bytes": (c_size_t, [c_int64]),
     "dodt_nms_state_offset": (c_size_t, [c_int64]),
-    "dodt_nms": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_float, c_int32,
+    "dodt_nms": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_float, c_int32, c_int32,
                          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 

@@ -27,9 +27,26 @@
 //                        The kept prefix is cut at max_out, appended to the output and to the
 //                        kept-box list that later windows test against.
 // Windows after the one that completes the selection exit immediately.
-#include <cub/device/device_radix_sort.cuh>
+//
+// Score order without a full sort. NMS consumes candidates in score order but (with max_out of
+// 1024 / 100) almost never looks past the first few thousand of the 10^4..10^5 candidates, so the
+// candidates are ordered lazily in chunks of kChunk = 2 windows:
+//   nms_select       one thread-block CLUSTER of 8 CTAs finds, by MSB-first radix selection on the
+//                    64-bit key (descending score, ascending index), the threshold below which
+//                    exactly the next kChunk candidates lie, and compacts them. Digit histograms
+//                    live in each CTA's shared memory and are combined through distributed shared
+//                    memory, one cluster barrier per digit; with tie-free scores three digits
+//                    (the 32 score bits) settle the threshold.
+//   nms_rank_gather  orders the chunk by counting: 16 lanes per candidate count how many of the
+//                    chunk's keys are smaller (keys staged in shared memory), which is the
+//                    candidate's rank; the lane group then writes the candidate's index, its
+//                    corner-normalised box and area at that rank. No sort network, no passes.
+// Sets of up to kChunk candidates (the final NMS) skip the selection.
+#include <cooperative_groups.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dodt {
 namespace {
@@ -40,6 +57,14 @@ constexpr int kTriWords = 64 * (kWords * (kWords + 1) / 2);  // triangular suppr
 constexpr int kRoundThreads = 1024;
 constexpr int kResolveThreads = kRoundThreads;
 constexpr int kPerThread = (kWin + kResolveThreads - 1) / kResolveThreads;  // candidates per thread
+constexpr int kChunkWins = 2;                // windows per lazily ordered chunk
+constexpr int kChunk = kChunkWins * kWin;    // 3072 candidates
+constexpr int kSelCluster = 8;               // CTAs per selection cluster
+constexpr int kSelThreads = 1024;
+constexpr int kSelBins = 2048;               // 11-bit digits
+constexpr int kRankThreads = 256;
+constexpr int kRankLanes = 16;               // lanes that share one candidate's count
+constexpr int kRankPerCta = kRankThreads / kRankLanes;
 
 struct NmsState {  // lives in the workspace, zeroed per call
   int n_kept;      // boxes selected so far
@@ -47,6 +72,7 @@ struct NmsState {  // lives in the workspace, zeroed per call
   unsigned tiles_done;  // CTA completion ticket of the current round
   int sweeps;           // relaxation sweeps of the last solved window (diagnostic)
   unsigned long long t_ns[6];  // globaltimer at phase boundaries of the last solved window (diagnostic)
+  unsigned long long bound;    // 64-bit keys below this are already ordered (end of the last chunk)
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -72,74 +98,155 @@ __device__ __forceinline__ bool iou_exceeds(const NmsBox &a, float area_a, const
   return iou > thr;
 }
 
-// sort keys (scores; -inf past the device-side candidate count so those sort last) + iota values
-__global__ void __launch_bounds__(256)
-nms_prepare(const float *__restrict__ scores, int n, const int *__restrict__ n_dev,
-            float *__restrict__ keys, int *__restrict__ idx) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
-  const int n_eff = n_dev ? min(n, __ldg(n_dev)) : n;
-  keys[i] = i < n_eff ? __ldg(scores + i) : -INFINITY;
-  idx[i] = i;
-}
-
-// boxes in score order, corners normalised, plus areas
-__global__ void __launch_bounds__(256)
-nms_gather(const float *__restrict__ boxes, const int *__restrict__ order, int n,
-           const int *__restrict__ n_dev, NmsBox *__restrict__ sbox, float *__restrict__ sarea) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= (n_dev ? min(n, __ldg(n_dev)) : n)) return;
-  const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + __ldg(order + i));
-  NmsBox o;
-  o.ymin = fminf(b.x, b.z); o.xmin = fminf(b.y, b.w);
-  o.ymax = fmaxf(b.x, b.z); o.xmax = fmaxf(b.y, b.w);
-  sbox[i] = o;
-  sarea[i] = __fmul_rn(__fsub_rn(o.ymax, o.ymin), __fsub_rn(o.xmax, o.xmin));
-}
-
-// Candidate sets of up to kSmallSort boxes (the final NMS: 1024 proposals) are ordered by one CTA
-// with a bitonic network in shared memory on the 64-bit key (descending score, ascending index)
-// and written out already gathered — one launch instead of prepare + radix sort + gather.
-constexpr int kSmallSort = 4096;
-
 __device__ __forceinline__ unsigned desc_key(float f) {
   const unsigned u = __float_as_uint(f);
   const unsigned asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending float order
   return ~asc;                                                       // smaller = higher score
 }
+// total order of the candidates: descending score, then ascending index (all keys distinct)
+__device__ __forceinline__ unsigned long long cand_key(float score, int i) {
+  return (static_cast<unsigned long long>(desc_key(score)) << 32) | static_cast<unsigned>(i);
+}
 
-__global__ void __launch_bounds__(1024)
-nms_sort_small(const float *__restrict__ boxes, const float *__restrict__ scores, int n,
-               const int *__restrict__ n_dev, int padded, int *__restrict__ order,
-               NmsBox *__restrict__ sbox, float *__restrict__ sarea) {
-  __shared__ unsigned long long key[kSmallSort];
-  const int n_eff = n_dev ? min(n, __ldg(n_dev)) : n;
-  for (int i = threadIdx.x; i < padded; i += 1024)
-    key[i] = i < n_eff ? (static_cast<unsigned long long>(desc_key(__ldg(scores + i))) << 32) | static_cast<unsigned>(i)
-                       : ~0ull;
-  __syncthreads();
-  for (int k = 2; k <= padded; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < padded / 2; t += 1024) {
-        // t-th compare-exchange of this stage: lower index i has bit j clear
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int p = i | j;
-        const unsigned long long a = key[i], b = key[p];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) { key[i] = b; key[p] = a; }
+// Chunk `chunk` = the candidates of rank [chunk*kChunk, (chunk+1)*kChunk) in key order. Finds the
+// exclusive upper key bound T of the chunk (the lower bound is where the previous chunk ended) and
+// writes the chunk's keys, unordered, to cand[0 .. min(kChunk, remaining)).
+__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
+nms_select(const float *__restrict__ scores, int n_max, const int *__restrict__ n_dev, int chunk,
+           NmsState *__restrict__ st, unsigned long long *__restrict__ cand) {
+  __shared__ int hist[2][kSelBins];
+  __shared__ int warp_tot[kSelThreads / 32];
+  __shared__ int s_bin, s_excl;
+  __shared__ int s_count, s_pos;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = static_cast<int>(cluster.block_rank());
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (st->done) return;                                  // uniform over the cluster
+  const int n = n_dev ? min(n_max, __ldg(n_dev)) : n_max;
+  const int lo_rank = chunk * kChunk;
+  if (lo_rank >= n) return;                              // uniform
+  const unsigned long long lo_bound = st->bound;
+  const int remaining = n - lo_rank;                     // candidates with key >= lo_bound
+  const int stride = kSelCluster * kSelThreads;
+  const int first = crank * kSelThreads + tid;
+
+  unsigned long long T = ~0ull;                          // exclusive upper bound of the chunk
+  if (remaining > kChunk) {
+    // MSB-first radix selection of the key of rank kChunk among the keys >= lo_bound: after each
+    // digit the search continues inside one bin; it ends as soon as the wanted key is the
+    // smallest of its bin (k_rem == 0), because then "prefix with zero low bits" separates.
+    int k_rem = kChunk;
+    unsigned long long prefix = 0;
+    int bits = 0;
+    for (int p = 0; p < 6; ++p) {
+      const int w = (p % 3 == 2) ? 10 : 11;              // 11+11+10 score bits, 11+11+10 index bits
+      int *h = hist[p & 1];
+      for (int b = tid; b < kSelBins; b += kSelThreads) h[b] = 0;
+      __syncthreads();
+      const int shift = 64 - bits - w;
+      for (int i = first; i < n; i += stride) {
+        const unsigned long long c = cand_key(__ldg(scores + i), i);
+        if (c >= lo_bound && (bits == 0 || (c >> (64 - bits)) == prefix))
+          atomicAdd(&h[static_cast<int>(c >> shift) & ((1 << w) - 1)], 1);
+      }
+      cluster.sync();                                    // every CTA's histogram is complete
+      // cluster-wide totals of this thread's two bins, through distributed shared memory
+      int t0 = 0, t1 = 0;
+#pragma unroll
+      for (int r = 0; r < kSelCluster; ++r) {
+        const int2 v = *reinterpret_cast<const int2 *>(cluster.map_shared_rank(h, r) + 2 * tid);
+        t0 += v.x;
+        t1 += v.y;
+      }
+      // block-wide exclusive scan of t0 + t1
+      int incl = t0 + t1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        int v = warp_tot[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, v, d);
+          if (lane >= d) v += up;
+        }
+        warp_tot[lane] = v;                              // inclusive scan of the warp totals
       }
       __syncthreads();
+      const int excl = incl - (t0 + t1) + (warp ? warp_tot[warp - 1] : 0);
+      if (k_rem >= excl && k_rem < excl + t0) { s_bin = 2 * tid; s_excl = excl; }
+      else if (k_rem >= excl + t0 && k_rem < excl + t0 + t1) { s_bin = 2 * tid + 1; s_excl = excl + t0; }
+      __syncthreads();
+      prefix = (prefix << w) | static_cast<unsigned>(s_bin);
+      bits += w;
+      k_rem -= s_excl;
+      __syncthreads();                                   // s_bin / warp_tot are reused next digit
+      if (k_rem == 0) break;                             // every CTA computes the same values
     }
+    T = bits >= 64 ? prefix : prefix << (64 - bits);
   }
-  for (int i = threadIdx.x; i < n_eff; i += 1024) {
-    const int src = static_cast<int>(key[i] & 0xFFFFFFFFull);
-    order[i] = src;
+
+  // compaction of lo_bound <= key < T: count per CTA, offsets across the cluster, scatter
+  if (tid == 0) { s_count = 0; s_pos = 0; }
+  __syncthreads();
+  int mine = 0;
+  for (int i = first; i < n; i += stride) {
+    const unsigned long long c = cand_key(__ldg(scores + i), i);
+    mine += (c >= lo_bound && c < T) ? 1 : 0;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
+  if (lane == 0 && mine) atomicAdd(&s_count, mine);
+  cluster.sync();
+  int offset = 0;
+  for (int r = 0; r < crank; ++r) offset += *cluster.map_shared_rank(&s_count, r);
+  for (int i = first; i < n; i += stride) {
+    const unsigned long long c = cand_key(__ldg(scores + i), i);
+    if (c >= lo_bound && c < T) cand[offset + atomicAdd(&s_pos, 1)] = c;
+  }
+  cluster.sync();                                        // nobody still reads this CTA's shared memory
+  if (crank == 0 && tid == 0) st->bound = T;
+}
+
+// Orders one chunk by counting and writes index / normalised box / area at each candidate's rank.
+// cand == nullptr: the chunk is the whole input (n <= kChunk), keys are built from the scores.
+__global__ void __launch_bounds__(kRankThreads)
+nms_rank_gather(const float *__restrict__ boxes, const float *__restrict__ scores,
+                const unsigned long long *__restrict__ cand, int n_max,
+                const int *__restrict__ n_dev, int chunk, const NmsState *__restrict__ st,
+                int *__restrict__ order, NmsBox *__restrict__ sbox, float *__restrict__ sarea) {
+  __shared__ unsigned long long s_key[kChunk];   // 24 KB
+  if (st->done) return;
+  const int n = n_dev ? min(n_max, __ldg(n_dev)) : n_max;
+  const int lo_rank = chunk * kChunk;
+  const int m = min(kChunk, n - lo_rank);
+  if (static_cast<int>(blockIdx.x) * kRankPerCta >= m) return;
+  for (int j = threadIdx.x; j < m; j += kRankThreads)
+    s_key[j] = cand ? __ldcg(cand + j) : cand_key(__ldg(scores + j), j);
+  __syncthreads();
+  const int ci = blockIdx.x * kRankPerCta + threadIdx.x / kRankLanes;
+  const int sub = threadIdx.x % kRankLanes;
+  const bool active = ci < m;
+  const unsigned long long me = active ? s_key[ci] : 0ull;
+  int cnt = 0;
+  if (active)
+    for (int j = sub; j < m; j += kRankLanes) cnt += s_key[j] < me ? 1 : 0;
+#pragma unroll
+  for (int d = kRankLanes / 2; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if (active && sub == 0) {
+    const int pos = lo_rank + cnt;
+    const int src = static_cast<int>(me & 0xFFFFFFFFull);
+    order[pos] = src;
     const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + src);
     NmsBox o;
     o.ymin = fminf(b.x, b.z); o.xmin = fminf(b.y, b.w);
     o.ymax = fmaxf(b.x, b.z); o.xmax = fmaxf(b.y, b.w);
-    sbox[i] = o;
-    sarea[i] = __fmul_rn(__fsub_rn(o.ymax, o.ymin), __fsub_rn(o.xmax, o.xmin));
+    sbox[pos] = o;
+    sarea[pos] = __fmul_rn(__fsub_rn(o.ymax, o.ymin), __fsub_rn(o.xmax, o.xmin));
   }
 }
 
@@ -377,8 +484,7 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
 }
 
 struct NmsLayout {
-  size_t keys_in, keys_out, vals_in, vals_out, sbox, sarea, kbox, karea, sup, dead, state, cub, total;
-  size_t cub_bytes;
+  size_t order, sbox, sarea, kbox, karea, cand, sup, dead, state, total;
 };
 
 size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -387,29 +493,15 @@ int nms_layout(int64_t n, NmsLayout *L) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
   const size_t nn = static_cast<size_t>(n > 0 ? n : 1);
-  L->keys_in = take(nn * 4);
-  L->keys_out = take(nn * 4);
-  L->vals_in = take(nn * 4);
-  L->vals_out = take(nn * 4);
+  L->order = take(nn * 4);
   L->sbox = take(nn * sizeof(NmsBox));
   L->sarea = take(nn * 4);
   L->kbox = take(nn * sizeof(NmsBox));
   L->karea = take(nn * 4);
+  L->cand = take(static_cast<size_t>(kChunk) * 8);
   L->sup = take(static_cast<size_t>(kTriWords) * 8);
   L->dead = take(2 * (kWin / 32) * 4);
   L->state = take(sizeof(NmsState));
-  size_t cub_bytes = 0;
-  cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(
-      nullptr, cub_bytes, static_cast<const float *>(nullptr), static_cast<float *>(nullptr),
-      static_cast<const int *>(nullptr), static_cast<int *>(nullptr), static_cast<int>(nn));
-  if (e != cudaSuccess) {
-    // no device (CPU-only host querying a size): CUB's size query needs none in practice, but
-    // stay conservative if it ever does
-    (void)cudaGetLastError();
-    cub_bytes = nn * 16 + (1u << 20);
-  }
-  L->cub_bytes = cub_bytes;
-  L->cub = take(cub_bytes);
   L->total = off;
   return DODT_OK;
 }
@@ -434,16 +526,21 @@ size_t dodt_nms_workspace_bytes(int64_t n) {
 }
 
 int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *n_dev,
-             int32_t max_out, float iou_threshold, int32_t max_windows, int32_t *keep,
+             int32_t max_out, float iou_threshold, int32_t first_window, int32_t max_windows,
+             int32_t *keep,
              int32_t *n_keep, void *workspace, size_t workspace_bytes, dodt_stream_t stream_) {
   using namespace dodt;
   if (n < 0 || n > 0x7FFFFFFF || max_out < 0 || max_windows < 0 || !n_keep || (max_out > 0 && !keep))
     return DODT_EINVAL;
+  if (first_window < 0 || first_window % dodt::kChunkWins != 0) return DODT_EINVAL;
+  const bool resume = first_window > 0;   // continue on the state a previous call left in `workspace`
   if (n > 0 && (!boxes || !scores)) return DODT_EINVAL;
   if (reinterpret_cast<uintptr_t>(boxes) % 16 != 0) return DODT_EALIGN;
   cudaStream_t stream = as_stream(stream_);
-  DODT_CUDA_TRY(cudaMemsetAsync(n_keep, 0, 2 * sizeof(int32_t), stream));
-  if (max_out > 0) DODT_CUDA_TRY(cudaMemsetAsync(keep, 0xFF, sizeof(int32_t) * max_out, stream));
+  if (!resume) {
+    DODT_CUDA_TRY(cudaMemsetAsync(n_keep, 0, 2 * sizeof(int32_t), stream));
+    if (max_out > 0) DODT_CUDA_TRY(cudaMemsetAsync(keep, 0xFF, sizeof(int32_t) * max_out, stream));
+  }
   if (n == 0 || max_out == 0) {
     // nothing to select: complete. One byte of 0x01 on the zeroed little-endian int32 is 1.
     DODT_CUDA_TRY(cudaMemsetAsync(n_keep + 1, 1, 1, stream));
@@ -454,36 +551,20 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *
   if (!workspace || workspace_bytes < L.total) return DODT_ECAPACITY;
   if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return DODT_EALIGN;
   char *ws = static_cast<char *>(workspace);
-  float *keys_in = reinterpret_cast<float *>(ws + L.keys_in);
-  float *keys_out = reinterpret_cast<float *>(ws + L.keys_out);
-  int *vals_in = reinterpret_cast<int *>(ws + L.vals_in);
-  int *order = reinterpret_cast<int *>(ws + L.vals_out);
+  int *order = reinterpret_cast<int *>(ws + L.order);
   NmsBox *sbox = reinterpret_cast<NmsBox *>(ws + L.sbox);
   float *sarea = reinterpret_cast<float *>(ws + L.sarea);
   NmsBox *kbox = reinterpret_cast<NmsBox *>(ws + L.kbox);
   float *karea = reinterpret_cast<float *>(ws + L.karea);
+  unsigned long long *cand = reinterpret_cast<unsigned long long *>(ws + L.cand);
   unsigned long long *sup = reinterpret_cast<unsigned long long *>(ws + L.sup);
   unsigned *dead = reinterpret_cast<unsigned *>(ws + L.dead);
   NmsState *st = reinterpret_cast<NmsState *>(ws + L.state);
 
   const int ni = static_cast<int>(n);
   // dead bits and state start at zero (one memset: they are adjacent up to alignment padding)
-  DODT_CUDA_TRY(cudaMemsetAsync(ws + L.dead, 0, (L.state - L.dead) + sizeof(NmsState), stream));
-  if (ni <= kSmallSort) {
-    int padded = 2;
-    while (padded < ni) padded <<= 1;
-    nms_sort_small<<<1, 1024, 0, stream>>>(boxes, scores, ni, n_dev, padded, order, sbox, sarea);
-    DODT_AFTER_LAUNCH();
-  } else {
-    nms_prepare<<<ceil_div(ni, 256), 256, 0, stream>>>(scores, ni, n_dev, keys_in, vals_in);
-    DODT_AFTER_LAUNCH();
-    size_t cub_bytes = L.cub_bytes;
-    DODT_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(ws + L.cub, cub_bytes, keys_in, keys_out,
-                                                            vals_in, order, ni, 0, 32, stream));
-    count_launch(6);  // CUB's histogram, scan and four onesweep passes (library kernels)
-    nms_gather<<<ceil_div(ni, 256), 256, 0, stream>>>(boxes, order, ni, n_dev, sbox, sarea);
-    DODT_AFTER_LAUNCH();
-  }
+  if (!resume)
+    DODT_CUDA_TRY(cudaMemsetAsync(ws + L.dead, 0, (L.state - L.dead) + sizeof(NmsState), stream));
 
   const size_t smem = static_cast<size_t>(kTriWords) * sizeof(unsigned long long);
   static bool attr_set = false;  // per process; the attribute is a property of the function
@@ -492,21 +573,35 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *
                                        static_cast<int>(smem)));
     attr_set = true;
   }
+  const bool lazy = ni > kChunk;   // more than one chunk: order the candidates chunk by chunk
   int windows = 0;
-  for (int base = 0; base < ni; base += kWin) {
-    if (max_windows > 0 && windows++ >= max_windows) break;
-    const int wcount = ni - base < kWin ? ni - base : kWin;
-    const int nb = (wcount + 63) / 64;
-    const int pb = (max_out + 63) / 64;  // upper bound of kept blocks from earlier windows
-    int tiles = nb * (nb + 1) / 2 + (base > 0 ? nb * pb : 0);
-    // the first window gets the whole GPU; later windows usually find the selection complete and
-    // exit, so they are launched narrower (cheaper no-op, still 10 tiles per CTA when they run)
-    const int cap = base == 0 ? 2 * kNumSMs : kNumSMs / 2;
-    const int grid = tiles < cap ? tiles : cap;
-    nms_round<<<grid, kRoundThreads, smem, stream>>>(sbox, sarea, order, ni, n_dev, base, max_out,
-                                                     iou_threshold, sup, dead, kbox, karea, st,
-                                                     keep, n_keep);
+  for (int chunk = first_window / kChunkWins; chunk * kChunk < ni; ++chunk) {
+    if (max_windows > 0 && windows >= max_windows) break;
+    const int cbase = chunk * kChunk;
+    const int m = ni - cbase < kChunk ? ni - cbase : kChunk;
+    if (lazy) {
+      nms_select<<<kSelCluster, kSelThreads, 0, stream>>>(scores, ni, n_dev, chunk, st, cand);
+      DODT_AFTER_LAUNCH();
+    }
+    nms_rank_gather<<<ceil_div(m, kRankPerCta), kRankThreads, 0, stream>>>(
+        boxes, scores, lazy ? cand : nullptr, ni, n_dev, chunk, st, order, sbox, sarea);
     DODT_AFTER_LAUNCH();
+    for (int base = cbase; base < cbase + m; base += kWin) {
+      if (max_windows > 0 && windows >= max_windows) break;
+      ++windows;
+      const int wcount = ni - base < kWin ? ni - base : kWin;
+      const int nb = (wcount + 63) / 64;
+      const int pb = (max_out + 63) / 64;  // upper bound of kept blocks from earlier windows
+      int tiles = nb * (nb + 1) / 2 + (base > 0 ? nb * pb : 0);
+      // the first window gets the whole GPU; later windows usually find the selection complete and
+      // exit, so they are launched narrower (cheaper no-op, still 10 tiles per CTA when they run)
+      const int cap = base == 0 ? 2 * kNumSMs : kNumSMs / 2;
+      const int grid = tiles < cap ? tiles : cap;
+      nms_round<<<grid, kRoundThreads, smem, stream>>>(sbox, sarea, order, ni, n_dev, base, max_out,
+                                                       iou_threshold, sup, dead, kbox, karea, st,
+                                                       keep, n_keep);
+      DODT_AFTER_LAUNCH();
+    }
   }
   return DODT_OK;
 }

@@ -327,10 +327,11 @@ def nms_workspace_bytes(n):
 
 
 def nms(boxes, scores, max_out, iou_threshold, keep=None, n_keep=None, workspace=None,
-        n_dev=None, max_windows=0):
+        n_dev=None, max_windows=0, first_window=0):
     """boxes [n,4] f32, scores [n] f32 -> (keep [max_out] i32 padded with -1, n_keep [2] i32:
     number selected, 1 if the selection is complete), both on the device (no synchronisation).
-    n_dev: optional device int32 candidate count; max_windows: see include/dodt_fe.h."""
+    n_dev: optional device int32 candidate count; max_windows / first_window: see
+    include/dodt_fe.h (bounded launch count, continuation of an incomplete selection)."""
     _need_cuda(boxes, scores, keep, n_keep, workspace, n_dev)
     if boxes.dim() != 2 or boxes.shape[1] != 4:
         raise ValueError("boxes must be 2-D [num_boxes, 4]")
@@ -352,6 +353,6 @@ def nms(boxes, scores, max_out, iou_threshold, keep=None, n_keep=None, workspace
     if workspace is None:
         workspace = torch.empty(max(nms_workspace_bytes(n), 256), dtype=torch.uint8, device=dev)
     check(load().dodt_nms(_ptr(boxes), _ptr(scores), n, _ptr(n_dev), max_out, float(iou_threshold),
-                          int(max_windows), _ptr(keep), _ptr(n_keep), _ptr(workspace),
+                          int(first_window), int(max_windows), _ptr(keep), _ptr(n_keep), _ptr(workspace),
                           workspace.numel(), _stream()), "dodt_nms")
     return keep, n_keep

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import ops
+from ._lib import NMS_CHUNK_WINDOWS, NMS_WINDOW
 
 
 def _dev(x, dtype):
@@ -43,7 +44,21 @@ def non_max_suppression(boxes, scores, max_output_size, iou_threshold=0.5, name=
     wrapper synchronises once to read it; use ops.nms for the fixed-shape device form."""
     bx, np_in = _dev(boxes, torch.float32)
     sc, _ = _dev(scores, torch.float32)
-    keep, n_keep = ops.nms(bx, sc, int(max_output_size), float(iou_threshold))
-    m = int(n_keep[0].item())
+    # Candidates are ordered lazily in score order; almost every selection completes within the
+    # first few windows, so windows are enqueued in growing batches and the completion flag is
+    # read between batches (the output length needs that read anyway).
+    n = bx.shape[0]
+    workspace = torch.empty(max(ops.nms_workspace_bytes(n), 256), dtype=torch.uint8, device=bx.device)
+    keep = n_keep = None
+    first, batch = 0, 2 * NMS_CHUNK_WINDOWS
+    while True:
+        keep, n_keep = ops.nms(bx, sc, int(max_output_size), float(iou_threshold), keep=keep,
+                               n_keep=n_keep, workspace=workspace, first_window=first,
+                               max_windows=batch)
+        m, complete = n_keep.cpu().tolist()
+        first += batch
+        if complete or first * NMS_WINDOW >= n:
+            break
+        batch *= 4
     sel = keep[:m]
     return sel.cpu().numpy() if np_in else sel

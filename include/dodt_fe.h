@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DODT_FE_VERSION 100 /* major*100 + minor */
+#define DODT_FE_VERSION 101 /* major*100 + minor */
 
 typedef void *dodt_stream_t; /* cudaStream_t */
 
@@ -214,19 +214,25 @@ int dodt_correlation(const float *a, const float *b, int32_t batch, int32_t heig
  * *n_keep are set to -1); n_keep: out int32 [1] on the device; suppress iff IoU > iou_threshold.
  * Equal scores are ordered by ascending index (TF leaves that order unspecified).
  * n_dev: optional device int32 — the candidate count is min(n, *n_dev) (entries past it are
- * ignored). max_windows: 0 = enqueue enough windows for any input; k > 0 = enqueue at most k
- * windows of DODT_NMS_WINDOW score-sorted candidates (fixed launch count for CUDA graphs); if the
- * selection is not complete after them n_keep[1] is set to 0, else 1. n_keep: out int32 [2].
+ * ignored). Candidates are visited in windows of DODT_NMS_WINDOW in score order, ordered lazily
+ * in chunks of DODT_NMS_CHUNK_WINDOWS windows. max_windows: 0 = enqueue enough windows for any
+ * input; k > 0 = enqueue at most k windows (fixed launch count for CUDA graphs); if the selection
+ * is not complete after them n_keep[1] is 0, else 1. n_keep: out int32 [2].
+ * first_window: 0 = new selection; a positive multiple of DODT_NMS_CHUNK_WINDOWS = continue the
+ * selection a previous, incomplete call left in the same workspace / keep / n_keep, starting at
+ * that window (same boxes, scores, n, max_out, threshold).
  * ---------------------------------------------------------------------------------------- */
 #define DODT_NMS_WINDOW 1536
+#define DODT_NMS_CHUNK_WINDOWS 2
 size_t dodt_nms_workspace_bytes(int64_t n);
 /* byte offset, inside the workspace, of the diagnostic block of the last solved window:
  * int32 {n_kept, done, ticket, sweeps} then uint64 globaltimer[6] {kernel start, IoU tiles done,
  * masks in shared memory, recurrence solved, emitted, -} */
 size_t dodt_nms_state_offset(int64_t n);
 int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *n_dev,
-             int32_t max_out, float iou_threshold, int32_t max_windows, int32_t *keep,
-             int32_t *n_keep, void *workspace, size_t workspace_bytes, dodt_stream_t stream);
+             int32_t max_out, float iou_threshold, int32_t first_window, int32_t max_windows,
+             int32_t *keep, int32_t *n_keep, void *workspace, size_t workspace_bytes,
+             dodt_stream_t stream);
 
 #ifdef __cplusplus
 }

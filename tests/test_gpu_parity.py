@@ -443,3 +443,38 @@ def test_nms_device_form_and_empty(dd):
     # degenerate (zero-area) boxes never suppress and are never suppressed
     z = torch.tensor([[0.5, 0.5, 0.5, 0.5]] * 3, dtype=torch.float32, device="cuda")
     assert dd.non_max_suppression(z, torch.tensor([0.3, 0.2, 0.1], device="cuda"), 3, 0.5).cpu().tolist() == [0, 1, 2]
+
+
+@pytest.mark.parametrize("n,levels", [(9000, 1), (9000, 3), (7000, 40), (3073, 2), (20000, 1500), (100, 1)])
+def test_nms_score_ties_across_chunks(dd, n, levels):
+    """Heavily tied scores: candidates are visited in (descending score, ascending index) order —
+    the stable order of the oracle — also where a run of equal scores straddles the 3072-candidate
+    chunks that the radix selection orders lazily (index digits of the 64-bit key decide)."""
+    rng = np.random.default_rng(n + levels)
+    boxes, _ = _nms_case(rng, n, max(n // 3, 1))
+    scores = (rng.integers(0, levels, n) / max(levels, 1)).astype(np.float32)
+    for max_out, thr in ((n, 0.5), (700, 0.8)):
+        np.testing.assert_array_equal(dd.non_max_suppression(boxes, scores, max_out, thr),
+                                      O.non_max_suppression(boxes, scores, max_out, thr))
+
+
+def test_nms_special_scores_and_device_count(dd):
+    """Negative scores, zeros of both signs and infinities order like the oracle's stable sort on
+    -scores; a device-side candidate count cuts the input at any position relative to the chunks."""
+    from dodt_b200 import ops
+    rng = np.random.default_rng(77)
+    n = 10000
+    boxes, scores = _nms_case(rng, n, 2500)
+    scores = (scores - 0.5).astype(np.float32)
+    scores[rng.choice(n, 50, replace=False)] = 0.0
+    scores[rng.choice(n, 5, replace=False)] = np.inf
+    scores[rng.choice(n, 5, replace=False)] = -np.inf
+    np.testing.assert_array_equal(dd.non_max_suppression(boxes, scores, 2000, 0.6),
+                                  O.non_max_suppression(boxes, scores, 2000, 0.6))
+    b, s = torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda()
+    for cut in (1, 1535, 3072, 3073, 6144, 6145, 9999):
+        n_dev = torch.tensor([cut], dtype=torch.int32, device="cuda")
+        keep, n_keep = ops.nms(b, s, 1500, 0.6, n_dev=n_dev)
+        want = O.non_max_suppression(boxes[:cut], scores[:cut], 1500, 0.6)
+        assert n_keep.cpu().tolist() == [len(want), 1], cut
+        np.testing.assert_array_equal(keep[:len(want)].cpu().numpy(), want)
