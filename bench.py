@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slots", type=int, default=3)
+    ap.add_argument("--slots", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -308,13 +308,24 @@ def run_ours(args):
     reps = max(20, min(K, 100))
 
     def time_stage(fn):
-        for i in range(3):
-            fn(slots[i % n_slots], slots[(i - 1) % n_slots])
+        """Mean device time of one stage: the stage is captured into a CUDA graph per slot (so the
+        Python/ctypes launch cost is not in the number) and the graphs are replayed back to back."""
+        for i in range(n_slots):
+            fn(slots[i], slots[i - 1])
+        torch.cuda.synchronize()
+        stage_graphs = []
+        for i in range(n_slots):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn(slots[i], slots[i - 1])
+            stage_graphs.append(g)
+        for g in stage_graphs:
+            g.replay()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(reps):
-            fn(slots[i % n_slots], slots[(i - 1) % n_slots])
+            stage_graphs[i % n_slots].replay()
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) * 1e3 / reps   # us
@@ -324,16 +335,23 @@ def run_ours(args):
         "S2_filter": lambda s, p: (ops.integral_image_2d(s.occ, s.ii, s.ws_ii),
                                    ops.anchor_filter_2d(fe.anchors, s.ii, fe.nx, fe.nz, fe.min_x, fe.min_z,
                                                         c.voxel_size, c.density_threshold, keep=s.keep),
-                                   ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact)),
-        "S3_rpn_crops": lambda s, p: (ops.crop_and_resize(s.bev_1ch, s.k_bev_boxes, None, c.rpn_crop, 0.0, out=s.rpn_bev_crops, n_dev=s.n_kept),
-                                      ops.crop_and_resize(s.img_1ch, s.k_img_boxes, None, c.rpn_crop, 0.0, out=s.rpn_img_crops, n_dev=s.n_kept)),
+                                   ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact),
+                                   ops.gather_rows_multi([(fe.anchor_bev_boxes, s.k_bev_boxes),
+                                                          (fe.anchor_img_boxes, s.k_img_boxes),
+                                                          (s.rpn_boxes, s.k_rpn_boxes),
+                                                          (s.rpn_img_boxes, s.k_rpn_img_boxes),
+                                                          (s.rpn_scores, s.k_rpn_scores)], s.kept_idx, s.n_kept)),
+        "S3_rpn_crops": lambda s, p: ops.crop_and_resize_multi([(s.bev_1ch, s.k_bev_boxes, s.rpn_bev_crops),
+                                                                (s.img_1ch, s.k_img_boxes, s.rpn_img_crops)],
+                                                               c.rpn_crop, 0.0, n_dev=s.n_kept),
         "S5_rpn_nms": lambda s, p: ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx,
                                            n_keep=s.n_top, workspace=s.ws_nms_rpn, n_dev=s.n_kept, max_windows=c.nms_max_windows),
         "S4_correlation": lambda s, p: ops.correlation(p.bev_feat, s.bev_feat, 1, c.corr_max_displacement, 1,
                                                        c.corr_stride_2, c.corr_padding, out=s.corr),
-        "S3_avod_crops": lambda s, p: (ops.crop_and_resize(s.bev_feat, s.prop_bev_boxes, None, c.avod_crop, 0.0, out=s.bev_rois, n_dev=s.n_top),
-                                       ops.crop_and_resize(s.img_feat, s.prop_img_boxes, None, c.avod_crop, 0.0, out=s.img_rois, n_dev=s.n_top),
-                                       ops.crop_and_resize(s.corr, s.prop_bev_boxes, None, c.avod_crop, 0.0, out=s.corr_rois, n_dev=s.n_top)),
+        "S3_avod_crops": lambda s, p: ops.crop_and_resize_multi([(s.bev_feat, s.prop_bev_boxes, s.bev_rois),
+                                                                 (s.img_feat, s.prop_img_boxes, s.img_rois),
+                                                                 (s.corr, s.prop_bev_boxes, s.corr_rois)],
+                                                                c.avod_crop, 0.0, n_dev=s.n_top),
         "S5_final_nms": lambda s, p: ops.nms(s.prop_bev_boxes, s.final_scores, c.avod_nms_size, c.avod_nms_iou, keep=s.final_idx,
                                              n_keep=s.n_final, workspace=s.ws_nms_final, n_dev=s.n_top),
     }

@@ -12,12 +12,20 @@
 // every operation individually rounded in fp32 (no FMA contraction), so tap selection and the
 // extrapolation decision are identical to the CPU op.
 //
-// Layout/mapping: one thread per output float4 (4 consecutive channels of one crop sample), so a
-// 32-channel sample is written by 8 adjacent lanes as one 128-byte line and each of the four taps
-// is read as one 128-byte line. Feature maps are far smaller than the 126 MB L2, so taps that
-// neighbouring ROIs share are served from L2; no shared-memory staging is used because a 7x7 crop
-// touches at most 196 of the several hundred pixels under its box (staging the box would read
-// more lines than the gather does).
+// Layout/mapping (crop_tables_kernel). A CTA owns R consecutive ROIs of one feature map:
+//   phase 1  the crop_h + crop_w axis coordinates of each ROI are evaluated ONCE (one thread per
+//            (ROI, axis, i)): tap offsets i0*stride / i1*stride, the lerp weight and the
+//            extrapolation flag go to a shared-memory table — the two fp32 divisions and the
+//            floor/ceil of the TF formula are not repeated per sample and per channel;
+//   phase 2  one thread per output float4 (C % 4 == 0) or float: two table reads, four adds, four
+//            128-bit tap loads, the individually rounded bilinear blend, one store. Consecutive
+//            lanes are consecutive channel vectors of one sample, so every tap and every output is
+//            a full 128-byte line for the 32-channel maps. Index decoding uses multiply-high by
+//            precomputed reciprocals (no integer division in the loop).
+// Feature maps are far smaller than the 126 MB L2, so taps that neighbouring ROIs share are served
+// from L2; no shared-memory staging of pixels is used because a 7x7 crop touches at most 196 of
+// the several hundred pixels under its box (staging the box would read more lines than the gather).
+// The element-per-thread kernel (crop_resize_kernel) remains for tensors beyond 2^31 elements.
 #include "common.cuh"
 
 namespace dodt {
@@ -112,64 +120,146 @@ crop_resize_kernel(const float *__restrict__ image, const float *__restrict__ bo
   }
 }
 
+constexpr int kCropThreads = 256;
+constexpr int kCropTableMax = 1024;   // axis-table entries per CTA (16 KB)
+
 struct CropMulti {
   const float *image[DODT_MAX_CROP_MAPS];
   const float *boxes[DODT_MAX_CROP_MAPS];
   float *crops[DODT_MAX_CROP_MAPS];
   int H[DODT_MAX_CROP_MAPS], W[DODT_MAX_CROP_MAPS], C[DODT_MAX_CROP_MAPS], vec[DODT_MAX_CROP_MAPS];
+  int rois_per_cta[DODT_MAX_CROP_MAPS];
+  unsigned mul_cv[DODT_MAX_CROP_MAPS];   // ceil(2^32 / (C / vec))
+  unsigned mul_s, mul_cw;                // ceil(2^32 / (crop_h*crop_w)), ceil(2^32 / crop_w)
   int batch, crop_h, crop_w;
   float extrap;
 };
 
-// blockIdx.y selects the map; every map uses its own channel vector width
-__global__ void __launch_bounds__(256)
-crop_resize_multi_kernel(const CropMulti m, const int *__restrict__ box_ind,
-                         const int *__restrict__ n_dev, long long n) {
-  const int s = blockIdx.y;
-  const int vec = m.vec[s];
+// n / d for n < 65536 through the precomputed reciprocal (exact: n * (mul*d - 2^32) < 2^32)
+// mul == 0 encodes d == 1 (2^32 does not fit)
+__device__ __forceinline__ int fast_div(int n, unsigned mul) {
+  return mul ? static_cast<int>(__umulhi(static_cast<unsigned>(n), mul)) : n;
+}
+
+template <int VEC>
+__device__ __forceinline__ void crop_tables_body(const CropMulti &m, int s,
+                                                 const int *__restrict__ box_ind, int n_eff,
+                                                 int4 *tab) {
   const int C = m.C[s], H = m.H[s], W = m.W[s];
-  const int cv = C / vec;
-  const long long total = n * m.crop_h * m.crop_w * cv;
-  const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (t >= total) return;
-  const int c = static_cast<int>(t % cv) * vec;
-  long long r = t / cv;
-  const int x = static_cast<int>(r % m.crop_w);
-  r /= m.crop_w;
-  const int y = static_cast<int>(r % m.crop_h);
-  const long long b = r / m.crop_h;
-  if (n_dev && b >= __ldg(n_dev)) return;
-  const int b_in = box_ind ? __ldg(box_ind + b) : 0;
-  if (b_in < 0 || b_in >= m.batch) return;
-  const float4 box = __ldg(reinterpret_cast<const float4 *>(m.boxes[s]) + b);
-  float *dst = m.crops[s] + t * vec;
-  int y0, y1i, x0, x1i;
-  float yl, xl;
-  const bool in_y = sample_coord(box.x, box.z, H, m.crop_h, y, &y0, &y1i, &yl);
-  const bool in_x = sample_coord(box.y, box.w, W, m.crop_w, x, &x0, &x1i, &xl);
-  const float *img = m.image[s] + static_cast<size_t>(b_in) * H * W * C + c;
-  if (vec == 4) {
-    float4 o = make_float4(m.extrap, m.extrap, m.extrap, m.extrap);
-    if (in_y && in_x) {
-      const float4 tl = __ldg(reinterpret_cast<const float4 *>(img + (static_cast<size_t>(y0) * W + x0) * C));
-      const float4 tr = __ldg(reinterpret_cast<const float4 *>(img + (static_cast<size_t>(y0) * W + x1i) * C));
-      const float4 bl = __ldg(reinterpret_cast<const float4 *>(img + (static_cast<size_t>(y1i) * W + x0) * C));
-      const float4 br = __ldg(reinterpret_cast<const float4 *>(img + (static_cast<size_t>(y1i) * W + x1i) * C));
-      o.x = bilerp(tl.x, tr.x, bl.x, br.x, xl, yl);
-      o.y = bilerp(tl.y, tr.y, bl.y, br.y, xl, yl);
-      o.z = bilerp(tl.z, tr.z, bl.z, br.z, xl, yl);
-      o.w = bilerp(tl.w, tr.w, bl.w, br.w, xl, yl);
+  const int ch = m.crop_h, cw = m.crop_w;
+  const int cv = C / VEC, S = ch * cw, axes = ch + cw;
+  const int R = m.rois_per_cta[s];
+  const int roi0 = blockIdx.x * R;
+  if (roi0 >= n_eff) return;
+  const int nr = min(R, n_eff - roi0);
+  const float4 *boxes = reinterpret_cast<const float4 *>(m.boxes[s]);
+
+  // ---- phase 1: axis tables
+  for (int e = threadIdx.x; e < nr * axes; e += kCropThreads) {
+    const int rl = e / axes, a = e - rl * axes;
+    const float4 box = __ldg(boxes + roi0 + rl);  // y1, x1, y2, x2
+    const bool is_y = a < ch;
+    int i0 = 0, i1 = 0;
+    float lerp = 0.0f;
+    const bool ok = is_y ? sample_coord(box.x, box.z, H, ch, a, &i0, &i1, &lerp)
+                         : sample_coord(box.y, box.w, W, cw, a - ch, &i0, &i1, &lerp);
+    int flag = ok ? 1 : 0;
+    int base = 0;
+    if (is_y) {
+      const int b_in = box_ind ? __ldg(box_ind + roi0 + rl) : 0;
+      if (b_in < 0 || b_in >= m.batch) flag = -1;   // TF leaves such rows untouched
+      else base = b_in * H * W * C;
     }
-    *reinterpret_cast<float4 *>(dst) = o;
-  } else {
-    float o = m.extrap;
-    if (in_y && in_x)
-      o = bilerp(__ldg(img + (static_cast<size_t>(y0) * W + x0) * C),
-                 __ldg(img + (static_cast<size_t>(y0) * W + x1i) * C),
-                 __ldg(img + (static_cast<size_t>(y1i) * W + x0) * C),
-                 __ldg(img + (static_cast<size_t>(y1i) * W + x1i) * C), xl, yl);
-    *dst = o;
+    const int stride = is_y ? W * C : C;
+    tab[e] = make_int4(base + i0 * stride, base + i1 * stride, __float_as_int(lerp), flag);
   }
+  __syncthreads();
+
+  // ---- phase 2: one thread per output vector
+  const float *img = m.image[s];
+  float *out = m.crops[s] + static_cast<size_t>(roi0) * S * C;
+  const int items = nr * S * cv;
+  const unsigned mul_cv = m.mul_cv[s];
+  for (int item = threadIdx.x; item < items; item += kCropThreads) {
+    const int slot = cv == 1 ? item : fast_div(item, mul_cv);
+    const int c = (item - slot * cv) * VEC;
+    const int rl = fast_div(slot, m.mul_s);
+    const int sidx = slot - rl * S;
+    const int y = fast_div(sidx, m.mul_cw);
+    const int x = sidx - y * cw;
+    const int4 ey = tab[rl * axes + y];
+    const int4 ex = tab[rl * axes + ch + x];
+    if (ey.w < 0) continue;
+    float *dst = out + slot * C + c;
+    const bool inside = ey.w > 0 && ex.w > 0;
+    const float yl = __int_as_float(ey.z), xl = __int_as_float(ex.z);
+    if (VEC == 4) {
+      float4 o = make_float4(m.extrap, m.extrap, m.extrap, m.extrap);
+      if (inside) {
+        const float *p = img + c;
+        const float4 tl = __ldg(reinterpret_cast<const float4 *>(p + ey.x + ex.x));
+        const float4 tr = __ldg(reinterpret_cast<const float4 *>(p + ey.x + ex.y));
+        const float4 bl = __ldg(reinterpret_cast<const float4 *>(p + ey.y + ex.x));
+        const float4 br = __ldg(reinterpret_cast<const float4 *>(p + ey.y + ex.y));
+        o.x = bilerp(tl.x, tr.x, bl.x, br.x, xl, yl);
+        o.y = bilerp(tl.y, tr.y, bl.y, br.y, xl, yl);
+        o.z = bilerp(tl.z, tr.z, bl.z, br.z, xl, yl);
+        o.w = bilerp(tl.w, tr.w, bl.w, br.w, xl, yl);
+      }
+      *reinterpret_cast<float4 *>(dst) = o;
+    } else {
+      float o = m.extrap;
+      if (inside) {
+        const float *p = img + c;
+        o = bilerp(__ldg(p + ey.x + ex.x), __ldg(p + ey.x + ex.y), __ldg(p + ey.y + ex.x),
+                   __ldg(p + ey.y + ex.y), xl, yl);
+      }
+      *dst = o;
+    }
+  }
+}
+
+// blockIdx.y selects the map; every map uses its own channel vector width and ROIs per CTA
+__global__ void __launch_bounds__(kCropThreads)
+crop_tables_kernel(const CropMulti m, const int *__restrict__ box_ind,
+                   const int *__restrict__ n_dev, int n) {
+  __shared__ int4 tab[kCropTableMax];
+  const int s = blockIdx.y;
+  const int n_eff = n_dev ? min(n, __ldg(n_dev)) : n;
+  if (m.vec[s] == 4) crop_tables_body<4>(m, s, box_ind, n_eff, tab);
+  else crop_tables_body<1>(m, s, box_ind, n_eff, tab);
+}
+
+unsigned recip32(int d) {
+  return d <= 1 ? 0u : static_cast<unsigned>(((1ull << 32) + d - 1) / static_cast<unsigned long long>(d));
+}
+
+// Fills the launch geometry of crop_tables_kernel; returns false if a map is outside its limits
+// (more than 2^31 elements, or one ROI needs more than 65535 items / kCropTableMax table entries).
+bool plan_tables(CropMulti *m, int n_specs, int64_t n, unsigned *grid_x) {
+  const int S = m->crop_h * m->crop_w, axes = m->crop_h + m->crop_w;
+  if (axes > kCropTableMax || n > 0x7FFFFFFF) return false;
+  m->mul_s = recip32(S);
+  m->mul_cw = recip32(m->crop_w);
+  long long gx = 0;
+  for (int k = 0; k < n_specs; ++k) {
+    const long long elems = static_cast<long long>(m->batch) * m->H[k] * m->W[k] * m->C[k];
+    const int cv = m->C[k] / m->vec[k];
+    const long long per_roi = static_cast<long long>(S) * cv;
+    if (elems >= 0x7FFFFFFFll || per_roi > 65535) return false;
+    int R = static_cast<int>((2 * kCropThreads + per_roi - 1) / per_roi);   // ~512 items per CTA
+    if (R < 1) R = 1;
+    if (R > kCropTableMax / axes) R = kCropTableMax / axes;
+    while (R > 1 && R * per_roi > 65535) --R;
+    m->rois_per_cta[k] = R;
+    m->mul_cv[k] = recip32(cv);
+    const long long g = (n + R - 1) / R;
+    if (g > gx) gx = g;
+  }
+  for (int k = n_specs; k < DODT_MAX_CROP_MAPS; ++k) { m->rois_per_cta[k] = 1; m->mul_cv[k] = 0; }
+  if (gx > 0x7FFFFFFFll) return false;
+  *grid_x = static_cast<unsigned>(gx);
+  return true;
 }
 
 }  // namespace
@@ -186,7 +276,6 @@ extern "C" int dodt_crop_and_resize_multi(const dodt_crop_spec *specs, int32_t n
   if (n == 0) return DODT_OK;
   CropMulti m;
   m.batch = batch; m.crop_h = crop_h; m.crop_w = crop_w; m.extrap = extrapolation_value;
-  long long max_threads = 0;
   for (int k = 0; k < DODT_MAX_CROP_MAPS; ++k) {
     const int j = k < n_specs ? k : 0;
     const dodt_crop_spec &sp = specs[j];
@@ -197,14 +286,27 @@ extern "C" int dodt_crop_and_resize_multi(const dodt_crop_spec *specs, int32_t n
     m.H[k] = sp.height; m.W[k] = sp.width; m.C[k] = sp.channels;
     m.vec[k] = (sp.channels % 4 == 0 && reinterpret_cast<uintptr_t>(sp.image) % 16 == 0 &&
                 reinterpret_cast<uintptr_t>(sp.crops) % 16 == 0) ? 4 : 1;
-    const long long th = static_cast<long long>(n) * crop_h * crop_w * (sp.channels / m.vec[k]);
-    if (k < n_specs && th > max_threads) max_threads = th;
   }
-  const long long blocks = (max_threads + 255) / 256;
-  if (blocks > 0x7FFFFFFFll) return DODT_ECAPACITY;
-  dim3 grid(static_cast<unsigned>(blocks), n_specs);
-  crop_resize_multi_kernel<<<grid, 256, 0, as_stream(stream_)>>>(m, box_ind, n_dev, n);
-  DODT_AFTER_LAUNCH();
+  cudaStream_t stream = as_stream(stream_);
+  unsigned grid_x = 0;
+  if (plan_tables(&m, n_specs, n, &grid_x)) {
+    dim3 grid(grid_x, n_specs);
+    crop_tables_kernel<<<grid, kCropThreads, 0, stream>>>(m, box_ind, n_dev, static_cast<int>(n));
+    DODT_AFTER_LAUNCH();
+    return DODT_OK;
+  }
+  // outside the table kernel's limits: one element-per-thread launch per map
+  for (int k = 0; k < n_specs; ++k) {
+    CropGeom g{batch, m.H[k], m.W[k], m.C[k], crop_h, crop_w, extrapolation_value};
+    const long long total = static_cast<long long>(n) * crop_h * crop_w * (m.C[k] / m.vec[k]);
+    const long long blocks = (total + 255) / 256;
+    if (blocks > 0x7FFFFFFFll) return DODT_ECAPACITY;
+    if (m.vec[k] == 4)
+      crop_resize_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(m.image[k], m.boxes[k], box_ind, n_dev, total, g, m.crops[k]);
+    else
+      crop_resize_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(m.image[k], m.boxes[k], box_ind, n_dev, total, g, m.crops[k]);
+    DODT_AFTER_LAUNCH();
+  }
   return DODT_OK;
 }
 
@@ -213,24 +315,14 @@ extern "C" int dodt_crop_and_resize(const float *image, int32_t batch, int32_t h
                                     const int32_t *box_ind, int64_t n, const int32_t *n_dev,
                                     int32_t crop_h, int32_t crop_w, float extrapolation_value,
                                     float *crops, dodt_stream_t stream_) {
-  using namespace dodt;
   if (n < 0 || batch <= 0 || height <= 0 || width <= 0 || channels <= 0 || crop_h <= 0 ||
       crop_w <= 0)
     return DODT_EINVAL;
   if (n == 0) return DODT_OK;
   if (!image || !boxes || !crops) return DODT_EINVAL;
-  if (reinterpret_cast<uintptr_t>(boxes) % 16 != 0) return DODT_EALIGN;
-  cudaStream_t stream = as_stream(stream_);
-  CropGeom g{batch, height, width, channels, crop_h, crop_w, extrapolation_value};
-  const bool vec4 = channels % 4 == 0 && reinterpret_cast<uintptr_t>(image) % 16 == 0 &&
-                    reinterpret_cast<uintptr_t>(crops) % 16 == 0;
-  const long long total = static_cast<long long>(n) * crop_h * crop_w * (vec4 ? channels / 4 : channels);
-  const long long blocks = (total + 255) / 256;
-  if (blocks > 0x7FFFFFFFll) return DODT_ECAPACITY;
-  if (vec4)
-    crop_resize_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(image, boxes, box_ind, n_dev, total, g, crops);
-  else
-    crop_resize_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(image, boxes, box_ind, n_dev, total, g, crops);
-  DODT_AFTER_LAUNCH();
-  return DODT_OK;
+  dodt_crop_spec sp;
+  sp.image = image; sp.boxes = boxes; sp.crops = crops;
+  sp.height = height; sp.width = width; sp.channels = channels; sp.reserved = 0;
+  return dodt_crop_and_resize_multi(&sp, 1, batch, box_ind, n, n_dev, crop_h, crop_w,
+                                    extrapolation_value, stream_);
 }

@@ -102,26 +102,32 @@ gather_rows(const float *__restrict__ src, int width, const int *__restrict__ id
 struct GatherMulti {
   const float *src[DODT_MAX_GATHER];
   float *dst[DODT_MAX_GATHER];
-  int col_end[DODT_MAX_GATHER];   // exclusive prefix of widths
+  int width[DODT_MAX_GATHER];
+  int vec4[DODT_MAX_GATHER];      // width % 4 == 0 and both arrays 16-byte aligned
   int n_specs;
-  int total_width;
 };
 
+// one thread per gathered row: the row index is read once, 4-float rows (boxes) move as float4
 __global__ void __launch_bounds__(256)
 gather_rows_multi(const GatherMulti g, const int *__restrict__ idx, const int *__restrict__ count,
-                  long long n_max) {
-  const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  const long long row = t / g.total_width;
-  int col = static_cast<int>(t % g.total_width);
+                  int n_max) {
+  const int row = blockIdx.x * 256 + threadIdx.x;
   if (row >= n_max || row >= __ldg(count)) return;
-  int s = 0, begin = 0;
+  const size_t srow = static_cast<size_t>(__ldg(idx + row));
 #pragma unroll
-  for (int k = 0; k < DODT_MAX_GATHER; ++k)
-    if (k < g.n_specs && col >= g.col_end[k]) { s = k + 1; begin = g.col_end[k]; }
-  col -= begin;
-  const int width = g.col_end[s] - begin;
-  const long long srow = __ldg(idx + row);
-  g.dst[s][row * width + col] = __ldg(g.src[s] + srow * width + col);
+  for (int k = 0; k < DODT_MAX_GATHER; ++k) {
+    if (k >= g.n_specs) break;
+    const int w = g.width[k];
+    if (g.vec4[k]) {
+      const float4 *sp = reinterpret_cast<const float4 *>(g.src[k] + srow * w);
+      float4 *dp = reinterpret_cast<float4 *>(g.dst[k] + static_cast<size_t>(row) * w);
+      for (int c = 0; c < w / 4; ++c) dp[c] = __ldg(sp + c);
+    } else {
+      const float *sp = g.src[k] + srow * w;
+      float *dp = g.dst[k] + static_cast<size_t>(row) * w;
+      for (int c = 0; c < w; ++c) dp[c] = __ldg(sp + c);
+    }
+  }
 }
 
 }  // namespace
@@ -135,26 +141,22 @@ int dodt_gather_rows_multi(const dodt_gather_spec *specs, int32_t n_specs, const
   if (!specs || n_specs <= 0 || n_specs > DODT_MAX_GATHER || n_max < 0 || !count) return DODT_EINVAL;
   if (n_max == 0) return DODT_OK;
   if (!idx) return DODT_EINVAL;
+  if (n_max > 0x7FFFFFFF) return DODT_ECAPACITY;
   GatherMulti g;
-  int total = 0;
   for (int k = 0; k < DODT_MAX_GATHER; ++k) {
+    g.src[k] = nullptr; g.dst[k] = nullptr; g.width[k] = 0; g.vec4[k] = 0;
     if (k < n_specs) {
       if (!specs[k].src || !specs[k].dst || specs[k].width <= 0) return DODT_EINVAL;
       g.src[k] = specs[k].src;
       g.dst[k] = specs[k].dst;
-      total += specs[k].width;
-    } else {
-      g.src[k] = nullptr;
-      g.dst[k] = nullptr;
+      g.width[k] = specs[k].width;
+      g.vec4[k] = specs[k].width % 4 == 0 && reinterpret_cast<uintptr_t>(specs[k].src) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(specs[k].dst) % 16 == 0;
     }
-    g.col_end[k] = total;
   }
   g.n_specs = n_specs;
-  g.total_width = total;
-  const long long threads = static_cast<long long>(n_max) * total;
-  const long long blocks = (threads + 255) / 256;
-  if (blocks > 0x7FFFFFFFll) return DODT_ECAPACITY;
-  gather_rows_multi<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream_)>>>(g, idx, count, n_max);
+  gather_rows_multi<<<ceil_div(n_max, 256), 256, 0, as_stream(stream_)>>>(g, idx, count,
+                                                                          static_cast<int>(n_max));
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }
