@@ -362,7 +362,7 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     corr_us = stage_us["S4_correlation"]            # one launch of corr_tile_k1 per call
     achieved = abytes["S4"] / (corr_us * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "corr_async_k1<2,4> (S4 correlation, %.0f%% of the step's "
+    roofline = {"bound": "hbm", "kernel": "corr_async_k1<2,4,0,8,2> (S4 correlation, %.0f%% of the step's "
                                           "algorithmic bytes)" % (100.0 * abytes["S4"] / abytes["total"]),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(), "peak_source": peak_src,

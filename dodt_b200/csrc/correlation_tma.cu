@@ -2,7 +2,9 @@
 // (kernel_size 1, stride_1 1, stride_2 2, neighbourhood radius R = max_displacement/2 in {1,2},
 // C % 8 == 0). See correlation.cu for the reference citations and the generic kernels.
 //
-// One persistent CTA per SM (grid = 148), 8 warps; thread 0 doubles as the TMA producer. Work unit = a 16 x 64 tile of output pixels x one chunk of 8 channels:
+// corr_tma_k1: one persistent CTA per SM (grid = 148), 8 warps; thread 0 doubles as the TMA
+// producer. Work unit = a 16 x 64 tile of output pixels x one chunk of 8 channels.
+// corr_async_k1 (default, further down): same math, fed by cp.async, 8 x 64 tiles, 2 CTAs per SM.
 //
 //   producer  cp.async.bulk.tensor.4d (TMA) loads the A tile [16 x 66 px x 8 ch] and the B tile
 //             with its 4-pixel halo [24 x 74 px x 8 ch] into one of two 90 KB stages; tile
@@ -41,24 +43,23 @@ constexpr int kConsumers = kTW / (2 * kPX) * 2 * kTH;  // 256
 // the two TMA loads of the NEXT work unit before it starts computing the current one.
 constexpr int kThreads = kConsumers;
 
-template <int R>
+template <int R, int TH = kTH>
 struct TmaCfg {
   static constexpr int WN = 2 * R + 1;
   static constexpr int D2 = WN * WN;
   static constexpr int HALO = 2 * R;                   // stride_2 == 2
   static constexpr int AW = kTW + 2;                   // pitch = 2 (mod 8)
   static constexpr int BW = ((kTW + 2 * HALO + 7) / 8) * 8 + 2;
-  static constexpr int BH = kTH + 2 * HALO;
-  static constexpr int A_BYTES = kTH * AW * kCC * 4;
+  static constexpr int BH = TH + 2 * HALO;
+  static constexpr int A_BYTES = TH * AW * kCC * 4;
   static constexpr int B_BYTES = BH * BW * kCC * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_PITCH = kTW * D2 + 2;       // floats; +2 keeps staging stores conflict-free
-  static constexpr int OUT_BYTES = kTH * OUT_PITCH * 4;
+  static constexpr int OUT_BYTES = TH * OUT_PITCH * 4;
   static constexpr int SPARE = OUT_BYTES > STAGE_BYTES ? OUT_BYTES - STAGE_BYTES : 0;
   static constexpr int STAGE1_OFF = ((STAGE_BYTES + SPARE + 1023) / 1024) * 1024;
   static constexpr int BAR_OFF = STAGE1_OFF + STAGE_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 64;
-  static_assert(A_BYTES % 1024 == 0, "B tile must stay 1024-byte aligned for the swizzle");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 corr_tma_k1(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const CorrTmaGeom g, float *__restrict__ out) {
   using Cfg = TmaCfg<R>;
+  static_assert(Cfg::A_BYTES % 1024 == 0, "B tile must stay 1024-byte aligned for the swizzle");
   constexpr int WN = Cfg::WN, D2 = Cfg::D2, NB = kPX + 2 * R;
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -258,19 +260,19 @@ struct CorrAsyncGeom {
 
 // PX pixels per thread (spaced 2 apart). PX = 4: 256 threads, 100 accumulators, 10 FMAs per
 // shared-memory float; PX = 2: 512 threads (16 warps), 50 accumulators, 6.7 FMAs per float.
-template <int R, int PX>
-__global__ void __launch_bounds__(kTW / (2 * PX) * 2 * kTH, 1)
+template <int R, int PX, int FRONT, int TH, int CTAS>
+__global__ void __launch_bounds__(kTW / (2 * PX) * 2 * TH, CTAS)
 corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const CorrAsyncGeom g,
               float *__restrict__ out) {
-  using Cfg = TmaCfg<R>;
+  using Cfg = TmaCfg<R, TH>;
   constexpr int WN = Cfg::WN, D2 = Cfg::D2, NB = PX + 2 * R;
-  constexpr int kThr = kTW / (2 * PX) * 2 * kTH;
+  constexpr int kThr = kTW / (2 * PX) * 2 * TH;
   constexpr int kWarps = kThr / 32;
   constexpr int kWX = kTW / (8 * PX);                   // warps along x
   constexpr int kBPieces = (kTW + 2 * Cfg::HALO) * 2;   // 16-byte pieces per B tile row
   constexpr int kAPieces = kTW * 2;
   constexpr int kRowThreads = kThr / 16;                // loader rows covered per pass
-  constexpr int kLoadRows = Cfg::BH + kTH;              // B rows then A rows
+  constexpr int kLoadRows = Cfg::BH + TH;               // B rows then A rows
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -310,7 +312,7 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
       const bool is_b = lr < Cfg::BH;
       const int trow = is_b ? lr : lr - Cfg::BH;
       const int halo = is_b ? Cfg::HALO : 0;
-      const int gy = ty * kTH + g.shift - halo + trow;
+      const int gy = ty * TH + g.shift - halo + trow;
       const int gx0 = tx * kTW + g.shift - halo + lpx;
       const bool row_ok = static_cast<unsigned>(gy) < static_cast<unsigned>(g.H);
       l_src[rr] = (is_b ? b : a) + img + (static_cast<long long>(gy) * g.W + gx0) * g.C + c0;
@@ -388,7 +390,13 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
                 sb + (boff[q] ^ (((p + half) & 1) << 2)) + p * 2 * Cfg::BW * kCC);
           // a few of the next unit's cp.async copies ride along with every math step, so the
           // LSU queue never sees a burst and the copies' latency hides behind the FMAs
-          if (more) issue_slice(half * WN + p);
+          if (FRONT) {
+            // all copies of the next unit go out during the first half of this unit's math, so
+            // the last of them has half a unit of FMAs to land behind
+            if (more && half == 0) { issue_slice(2 * p); issue_slice(2 * p + 1); }
+          } else {
+            if (more) issue_slice(half * WN + p);
+          }
 #pragma unroll
           for (int j = 0; j < PX; ++j)
 #pragma unroll
@@ -429,9 +437,9 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
       }
     }
     __syncthreads();
-    const int valid_rows = min(kTH, g.out_h - ty * kTH);
+    const int valid_rows = min(TH, g.out_h - ty * TH);
     const int valid_floats = min(kTW, g.out_w - tx * kTW) * D2;
-    float *gout = out + ((static_cast<size_t>(n) * g.out_h + ty * kTH) * g.out_w + tx * kTW) * D2;
+    float *gout = out + ((static_cast<size_t>(n) * g.out_h + ty * TH) * g.out_w + tx * kTW) * D2;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 8 == 0) && ((g.out_w * D2) % 2 == 0) &&
                         (valid_floats % 2 == 0);
     for (int r = warp; r < valid_rows; r += kWarps) {
@@ -509,26 +517,26 @@ int launch(const float *a, const float *b, int N, int H, int W, int C, int out_h
   return DODT_OK;
 }
 
-template <int R, int PX>
+template <int R, int PX, int FRONT, int TH = kTH, int CTAS = 1>
 int launch_async(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w,
                  int shift, float *out, cudaStream_t stream) {
-  using Cfg = TmaCfg<R>;
-  constexpr int kThr = kTW / (2 * PX) * 2 * kTH;
+  using Cfg = TmaCfg<R, TH>;
+  constexpr int kThr = kTW / (2 * PX) * 2 * TH;
   static bool attr_set = false;
   if (!attr_set) {
-    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R, PX>,
+    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R, PX, FRONT, TH, CTAS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   CorrAsyncGeom g;
   g.batch = N; g.H = H; g.W = W; g.C = C; g.out_h = out_h; g.out_w = out_w; g.shift = shift;
   g.tiles_x = ceil_div(out_w, kTW);
-  g.tiles_y = ceil_div(out_h, kTH);
+  g.tiles_y = ceil_div(out_h, TH);
   g.n_tiles = g.tiles_x * g.tiles_y * N;
   g.pow2 = (C & (C - 1)) == 0 ? 1 : 0;
   g.inv_c = 1.0f / static_cast<float>(C);
-  const int grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
-  corr_async_k1<R, PX><<<grid, kThr, Cfg::SMEM_BYTES, stream>>>(a, b, g, out);
+  const int grid = g.n_tiles < CTAS * kNumSMs ? g.n_tiles : CTAS * kNumSMs;
+  corr_async_k1<R, PX, FRONT, TH, CTAS><<<grid, kThr, Cfg::SMEM_BYTES, stream>>>(a, b, g, out);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }
@@ -545,7 +553,7 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
   static int impl = -1;
   if (impl < 0) {
     const char *e = getenv("DODT_CORR_IMPL");
-    impl = (e && e[0] == 't') ? 1 : ((e && e[0] == '2') ? 2 : 0);
+    impl = (e && e[0] == 't') ? 1 : ((e && e[0] == '2') ? 2 : ((e && e[0] == 'f') ? 3 : ((e && e[0] == '1') ? 4 : 0)));
   }
   if (impl == 1) {
     switch (r) {
@@ -556,14 +564,30 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
   }
   if (impl == 2) {   // 16 warps x 2 pixels per thread
     switch (r) {
-      case 1: return launch_async<1, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
-      case 2: return launch_async<2, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      case 1: return launch_async<1, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      case 2: return launch_async<2, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
       default: return 1;
     }
   }
+  if (impl == 3) {   // next unit's copies issued in the first half of the unit (A/B timing: slower)
+    switch (r) {
+      case 1: return launch_async<1, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      case 2: return launch_async<2, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      default: return 1;
+    }
+  }
+  if (impl == 4) {   // 16-row tiles, 8 warps, one CTA per SM (A/B timing: 68 us vs 59 us)
+    switch (r) {
+      case 1: return launch_async<1, 4, 0>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      case 2: return launch_async<2, 4, 0>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      default: return 1;
+    }
+  }
+  // default: 8-row tiles, 4 warps per CTA, TWO CTAs per SM — the per-unit barrier, the exposed
+  // tail of the copies and the epilogue of one CTA hide behind the other CTA's math
   switch (r) {
-    case 1: return launch_async<1, 4>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
-    case 2: return launch_async<2, 4>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+    case 1: return launch_async<1, 4, 0, 8, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+    case 2: return launch_async<2, 4, 0, 8, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
     default: return 1;
   }
 }
