@@ -33,10 +33,10 @@
 // candidates are ordered lazily in chunks of kChunk = 2 windows:
 //   nms_select       one thread-block CLUSTER of 8 CTAs finds, by MSB-first radix selection on the
 //                    64-bit key (descending score, ascending index), the threshold below which
-//                    exactly the next kChunk candidates lie, and compacts them. Digit histograms
-//                    live in each CTA's shared memory and are combined through distributed shared
-//                    memory, one cluster barrier per digit; with tie-free scores three digits
-//                    (the 32 score bits) settle the threshold.
+//                    exactly the next kChunk candidates lie, and compacts them. Score keys stay
+//                    in registers; the 256-bin digit histograms live in each CTA's shared memory
+//                    and are combined through distributed shared memory, one cluster barrier per
+//                    digit; with tie-free scores the four score digits settle the threshold.
 //   nms_rank_gather  orders the chunk by counting: 16 lanes per candidate count how many of the
 //                    chunk's keys are smaller (keys staged in shared memory), which is the
 //                    candidate's rank; the lane group then writes the candidate's index, its
@@ -61,10 +61,12 @@ constexpr int kChunkWins = 2;                // windows per lazily ordered chunk
 constexpr int kChunk = kChunkWins * kWin;    // 3072 candidates
 constexpr int kSelCluster = 8;               // CTAs per selection cluster
 constexpr int kSelThreads = 1024;
-constexpr int kSelBins = 2048;               // 11-bit digits
+constexpr int kSelBins = 256;                // 8-bit digits
+constexpr int kSelCache = 12;                // score keys a thread keeps in registers
 constexpr int kRankThreads = 256;
 constexpr int kRankLanes = 16;               // lanes that share one candidate's count
-constexpr int kRankPerCta = kRankThreads / kRankLanes;
+constexpr int kRankEach = 2;                 // candidates counted by one lane group (shared key loads)
+constexpr int kRankPerCta = kRankEach * kRankThreads / kRankLanes;
 
 struct NmsState {  // lives in the workspace, zeroed per call
   int n_kept;      // boxes selected so far
@@ -111,11 +113,13 @@ __device__ __forceinline__ unsigned long long cand_key(float score, int i) {
 // Chunk `chunk` = the candidates of rank [chunk*kChunk, (chunk+1)*kChunk) in key order. Finds the
 // exclusive upper key bound T of the chunk (the lower bound is where the previous chunk ended) and
 // writes the chunk's keys, unordered, to cand[0 .. min(kChunk, remaining)).
+// CACHED: every thread keeps its (at most kSelCache) score keys in registers across the digits.
+template <bool CACHED>
 __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 nms_select(const float *__restrict__ scores, int n_max, const int *__restrict__ n_dev, int chunk,
            NmsState *__restrict__ st, unsigned long long *__restrict__ cand) {
   __shared__ int hist[2][kSelBins];
-  __shared__ int warp_tot[kSelThreads / 32];
+  __shared__ int warp_tot[kSelBins / 32];
   __shared__ int s_bin, s_excl;
   __shared__ int s_count, s_pos;
   cg::cluster_group cluster = cg::this_cluster();
@@ -127,62 +131,82 @@ nms_select(const float *__restrict__ scores, int n_max, const int *__restrict__ 
   if (lo_rank >= n) return;                              // uniform
   const unsigned long long lo_bound = st->bound;
   const int remaining = n - lo_rank;                     // candidates with key >= lo_bound
-  const int stride = kSelCluster * kSelThreads;
+  constexpr int stride = kSelCluster * kSelThreads;
   const int first = crank * kSelThreads + tid;
+  const int iters = (n + stride - 1) / stride;           // uniform trip count
+
+  unsigned key[kSelCache];
+  if (CACHED) {
+#pragma unroll
+    for (int e = 0; e < kSelCache; ++e) {
+      const int i = first + e * stride;
+      key[e] = (e < iters && i < n) ? desc_key(__ldg(scores + i)) : 0u;
+    }
+  }
+  // 64-bit key of this thread's e-th candidate; false when there is none or it is below lo_bound
+  auto fetch = [&](int e, unsigned long long *c) {
+    const int i = first + e * stride;
+    if (i >= n) return false;
+    const unsigned k = CACHED ? key[e] : desc_key(__ldg(scores + i));
+    *c = (static_cast<unsigned long long>(k) << 32) | static_cast<unsigned>(i);
+    return *c >= lo_bound;
+  };
 
   unsigned long long T = ~0ull;                          // exclusive upper bound of the chunk
   if (remaining > kChunk) {
-    // MSB-first radix selection of the key of rank kChunk among the keys >= lo_bound: after each
-    // digit the search continues inside one bin; it ends as soon as the wanted key is the
-    // smallest of its bin (k_rem == 0), because then "prefix with zero low bits" separates.
+    // MSB-first radix selection (8-bit digits) of the key of rank kChunk among the keys >=
+    // lo_bound: after each digit the search continues inside one bin; it ends as soon as the
+    // wanted key is the smallest of its bin (k_rem == 0), because then "prefix with zero low
+    // bits" separates. Tie-free scores settle within the four score digits.
     int k_rem = kChunk;
     unsigned long long prefix = 0;
     int bits = 0;
-    for (int p = 0; p < 6; ++p) {
-      const int w = (p % 3 == 2) ? 10 : 11;              // 11+11+10 score bits, 11+11+10 index bits
+    for (int p = 0; p < 8; ++p) {
       int *h = hist[p & 1];
-      for (int b = tid; b < kSelBins; b += kSelThreads) h[b] = 0;
+      if (tid < kSelBins) h[tid] = 0;
       __syncthreads();
-      const int shift = 64 - bits - w;
-      for (int i = first; i < n; i += stride) {
-        const unsigned long long c = cand_key(__ldg(scores + i), i);
-        if (c >= lo_bound && (bits == 0 || (c >> (64 - bits)) == prefix))
-          atomicAdd(&h[static_cast<int>(c >> shift) & ((1 << w) - 1)], 1);
+      const int shift = 56 - bits;
+      // Scores of real candidates crowd into a few high-digit bins (floats of one octave share
+      // sign, exponent and leading mantissa bits), so the lanes of a warp first combine equal
+      // bins (match.any) and one lane per distinct bin adds the group's count.
+#pragma unroll
+      for (int e = 0; e < (CACHED ? kSelCache : 1); ++e) {
+        for (int ee = e; ee < iters; ee += (CACHED ? iters : 1)) {   // CACHED: exactly once
+          unsigned long long c = 0;
+          bool part = fetch(ee, &c);
+          part = part && (bits == 0 || (c >> (64 - bits)) == prefix);
+          const int bin = static_cast<int>(c >> shift) & (kSelBins - 1);
+          const unsigned active = __ballot_sync(0xffffffffu, part);
+          if (part) {
+            const unsigned peers = __match_any_sync(active, bin);
+            if (lane == __ffs(peers) - 1) atomicAdd(&h[bin], __popc(peers));
+          }
+        }
       }
       cluster.sync();                                    // every CTA's histogram is complete
-      // cluster-wide totals of this thread's two bins, through distributed shared memory
-      int t0 = 0, t1 = 0;
+      // cluster-wide total of bin `tid` through distributed shared memory, then a block scan
+      int t = 0;
+      if (tid < kSelBins) {
 #pragma unroll
-      for (int r = 0; r < kSelCluster; ++r) {
-        const int2 v = *reinterpret_cast<const int2 *>(cluster.map_shared_rank(h, r) + 2 * tid);
-        t0 += v.x;
-        t1 += v.y;
+        for (int r = 0; r < kSelCluster; ++r) t += cluster.map_shared_rank(h, r)[tid];
       }
-      // block-wide exclusive scan of t0 + t1
-      int incl = t0 + t1;
+      int incl = t;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const int up = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += up;
       }
-      if (lane == 31) warp_tot[warp] = incl;
+      if (tid < kSelBins && lane == 31) warp_tot[warp] = incl;
       __syncthreads();
-      if (warp == 0) {
-        int v = warp_tot[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int up = __shfl_up_sync(0xffffffffu, v, d);
-          if (lane >= d) v += up;
-        }
-        warp_tot[lane] = v;                              // inclusive scan of the warp totals
+      if (tid < kSelBins) {
+        int before = 0;
+        for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
+        const int excl = before + incl - t;
+        if (k_rem >= excl && k_rem < excl + t) { s_bin = tid; s_excl = excl; }
       }
       __syncthreads();
-      const int excl = incl - (t0 + t1) + (warp ? warp_tot[warp - 1] : 0);
-      if (k_rem >= excl && k_rem < excl + t0) { s_bin = 2 * tid; s_excl = excl; }
-      else if (k_rem >= excl + t0 && k_rem < excl + t0 + t1) { s_bin = 2 * tid + 1; s_excl = excl + t0; }
-      __syncthreads();
-      prefix = (prefix << w) | static_cast<unsigned>(s_bin);
-      bits += w;
+      prefix = (prefix << 8) | static_cast<unsigned>(s_bin);
+      bits += 8;
       k_rem -= s_excl;
       __syncthreads();                                   // s_bin / warp_tot are reused next digit
       if (k_rem == 0) break;                             // every CTA computes the same values
@@ -194,20 +218,24 @@ nms_select(const float *__restrict__ scores, int n_max, const int *__restrict__ 
   if (tid == 0) { s_count = 0; s_pos = 0; }
   __syncthreads();
   int mine = 0;
-  for (int i = first; i < n; i += stride) {
-    const unsigned long long c = cand_key(__ldg(scores + i), i);
-    mine += (c >= lo_bound && c < T) ? 1 : 0;
-  }
+#pragma unroll
+  for (int e = 0; e < (CACHED ? kSelCache : 1); ++e)
+    for (int ee = e; ee < iters; ee += (CACHED ? iters : 1)) {
+      unsigned long long c = 0;
+      mine += (fetch(ee, &c) && c < T) ? 1 : 0;
+    }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
   if (lane == 0 && mine) atomicAdd(&s_count, mine);
   cluster.sync();
   int offset = 0;
   for (int r = 0; r < crank; ++r) offset += *cluster.map_shared_rank(&s_count, r);
-  for (int i = first; i < n; i += stride) {
-    const unsigned long long c = cand_key(__ldg(scores + i), i);
-    if (c >= lo_bound && c < T) cand[offset + atomicAdd(&s_pos, 1)] = c;
-  }
+#pragma unroll
+  for (int e = 0; e < (CACHED ? kSelCache : 1); ++e)
+    for (int ee = e; ee < iters; ee += (CACHED ? iters : 1)) {
+      unsigned long long c = 0;
+      if (fetch(ee, &c) && c < T) cand[offset + atomicAdd(&s_pos, 1)] = c;
+    }
   cluster.sync();                                        // nobody still reads this CTA's shared memory
   if (crank == 0 && tid == 0) st->bound = T;
 }
@@ -225,21 +253,34 @@ nms_rank_gather(const float *__restrict__ boxes, const float *__restrict__ score
   const int lo_rank = chunk * kChunk;
   const int m = min(kChunk, n - lo_rank);
   if (static_cast<int>(blockIdx.x) * kRankPerCta >= m) return;
+#pragma unroll 4
   for (int j = threadIdx.x; j < m; j += kRankThreads)
     s_key[j] = cand ? __ldcg(cand + j) : cand_key(__ldg(scores + j), j);
   __syncthreads();
-  const int ci = blockIdx.x * kRankPerCta + threadIdx.x / kRankLanes;
   const int sub = threadIdx.x % kRankLanes;
-  const bool active = ci < m;
-  const unsigned long long me = active ? s_key[ci] : 0ull;
-  int cnt = 0;
-  if (active)
-    for (int j = sub; j < m; j += kRankLanes) cnt += s_key[j] < me ? 1 : 0;
+  const int c0 = blockIdx.x * kRankPerCta + (threadIdx.x / kRankLanes) * kRankEach;
+  unsigned long long me[kRankEach];
+  int cnt[kRankEach];
 #pragma unroll
-  for (int d = kRankLanes / 2; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-  if (active && sub == 0) {
-    const int pos = lo_rank + cnt;
-    const int src = static_cast<int>(me & 0xFFFFFFFFull);
+  for (int e = 0; e < kRankEach; ++e) {
+    me[e] = c0 + e < m ? s_key[c0 + e] : 0ull;   // key 0 never occurs: nothing is smaller
+    cnt[e] = 0;
+  }
+#pragma unroll 8
+  for (int j = sub; j < m; j += kRankLanes) {
+    const unsigned long long k = s_key[j];
+#pragma unroll
+    for (int e = 0; e < kRankEach; ++e) cnt[e] += k < me[e] ? 1 : 0;
+  }
+#pragma unroll
+  for (int e = 0; e < kRankEach; ++e)
+#pragma unroll
+    for (int d = kRankLanes / 2; d > 0; d >>= 1) cnt[e] += __shfl_xor_sync(0xffffffffu, cnt[e], d);
+#pragma unroll
+  for (int e = 0; e < kRankEach; ++e) {
+    if (sub != e || c0 + e >= m) continue;      // lane e of the group writes candidate e
+    const int pos = lo_rank + cnt[e];
+    const int src = static_cast<int>(me[e] & 0xFFFFFFFFull);
     order[pos] = src;
     const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + src);
     NmsBox o;
@@ -266,7 +307,9 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
           int max_out, float thr,
           unsigned long long *__restrict__ sup,      // [kTriWords] suppressor bitmasks
           unsigned *__restrict__ dead,               // [2*kWin/32]: killed by earlier windows,
-                                                     // then "has a suppressor in this window"
+                                                     // then "has a suppressor in this window";
+                                                     // then [kWin]: which suppressor words of
+                                                     // each candidate are non-zero
           NmsBox *__restrict__ kbox, float *__restrict__ karea,  // kept boxes so far
           NmsState *__restrict__ st, int *__restrict__ keep, int *__restrict__ n_keep) {
   extern __shared__ unsigned long long smem_sup[];   // phase 2: [kTriWords]
@@ -338,8 +381,11 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
         if (vs_prev) {
           if (m0 | m1) atomicOr(&dead[i >> 5], 1u << (i & 31));
         } else {
-          sup[tri_word(i, bj)] = (static_cast<unsigned long long>(m1) << 32) | m0;
-          if (m0 | m1) atomicOr(&dead[kWin / 32 + (i >> 5)], 1u << (i & 31));
+          if (m0 | m1) {
+            sup[tri_word(i, bj)] = (static_cast<unsigned long long>(m1) << 32) | m0;
+            atomicOr(&dead[kWin / 32 + (i >> 5)], 1u << (i & 31));
+            atomicOr(&dead[2 * (kWin / 32) + i], 1u << bj);
+          }
         }
       }
     }
@@ -358,17 +404,18 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
   if (threadIdx.x == 0) { st->t_ns[0] = t_start; st->t_ns[1] = global_ns(); }
 
   // ---------------- phase 2: solve the window ----------------
-  const int used_words = 64 * (nb * (nb + 1) / 2);
-  {
-    int w = threadIdx.x;
-    for (; w + 3 * kResolveThreads < used_words; w += 4 * kResolveThreads) {
-      const unsigned long long v0 = __ldcg(sup + w), v1 = __ldcg(sup + w + kResolveThreads),
-                               v2 = __ldcg(sup + w + 2 * kResolveThreads),
-                               v3 = __ldcg(sup + w + 3 * kResolveThreads);
-      smem_sup[w] = v0; smem_sup[w + kResolveThreads] = v1;
-      smem_sup[w + 2 * kResolveThreads] = v2; smem_sup[w + 3 * kResolveThreads] = v3;
+  // only the suppressor words that hold a bit are fetched (at IoU 0.8 that is a few per cent of
+  // the 225 KB triangle); a thread reads back only the words it fetched itself
+  unsigned nz[kPerThread];
+#pragma unroll
+  for (int q = 0; q < kPerThread; ++q) {
+    const int i = q * kResolveThreads + threadIdx.x;
+    nz[q] = i < wcount ? __ldcg(dead + 2 * (kWin / 32) + i) : 0u;
+    const int row = tri_base(i < kWin ? i : 0);
+    for (unsigned m = nz[q]; m; m &= m - 1) {
+      const int w = __ffs(m) - 1;
+      smem_sup[row + w * 64] = __ldcg(sup + row + w * 64);
     }
-    for (; w < used_words; w += kResolveThreads) smem_sup[w] = __ldcg(sup + w);
   }
   if (threadIdx.x < kWords) {
     const int w = threadIdx.x;
@@ -392,9 +439,6 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
 #pragma unroll
   for (int q = 0; q < kPerThread; ++q) undecided[q] = true;
   int sweeps = 0;
-  unsigned nz[kPerThread];
-#pragma unroll
-  for (int q = 0; q < kPerThread; ++q) nz[q] = 0;
   while (true) {
     ++sweeps;
     int pending = 0;
@@ -410,13 +454,6 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
         continue;
       }
       const unsigned long long *row = smem_sup + tri_base(i);
-      if (sweeps == 1) {   // remember which of the candidate's words hold any suppressor at all
-        const int bi = i >> 6;
-        unsigned m = 0;
-        for (int w = 0; w <= bi; ++w)
-          if (row[w * 64]) m |= 1u << w;
-        nz[q] = m;
-      }
       bool hit_kept = false, all_removed = true;
       for (unsigned m = nz[q]; m; m &= m - 1) {
         const int w = __ffs(m) - 1;
@@ -467,7 +504,7 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
     }
   }
   // reset the per-round scratch for the next window
-  for (int w = threadIdx.x; w < 2 * (kWin / 32); w += kResolveThreads) dead[w] = 0u;
+  for (int w = threadIdx.x; w < 2 * (kWin / 32) + kWin; w += kResolveThreads) dead[w] = 0u;
   __syncthreads();
   if (threadIdx.x == 0) {
     const int total = min(max_out, n_prev + s_prefix[kWords]);
@@ -500,7 +537,7 @@ int nms_layout(int64_t n, NmsLayout *L) {
   L->karea = take(nn * 4);
   L->cand = take(static_cast<size_t>(kChunk) * 8);
   L->sup = take(static_cast<size_t>(kTriWords) * 8);
-  L->dead = take(2 * (kWin / 32) * 4);
+  L->dead = take((2 * (kWin / 32) + kWin) * 4);
   L->state = take(sizeof(NmsState));
   L->total = off;
   return DODT_OK;
@@ -580,7 +617,10 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *
     const int cbase = chunk * kChunk;
     const int m = ni - cbase < kChunk ? ni - cbase : kChunk;
     if (lazy) {
-      nms_select<<<kSelCluster, kSelThreads, 0, stream>>>(scores, ni, n_dev, chunk, st, cand);
+      if (ni <= kSelCache * kSelCluster * kSelThreads)
+        nms_select<true><<<kSelCluster, kSelThreads, 0, stream>>>(scores, ni, n_dev, chunk, st, cand);
+      else
+        nms_select<false><<<kSelCluster, kSelThreads, 0, stream>>>(scores, ni, n_dev, chunk, st, cand);
       DODT_AFTER_LAUNCH();
     }
     nms_rank_gather<<<ceil_div(m, kRankPerCta), kRankThreads, 0, stream>>>(
