@@ -301,26 +301,23 @@ __device__ __forceinline__ int tri_base(int i) {
 }
 __device__ __forceinline__ int tri_word(int i, int w) { return tri_base(i) + w * 64; }
 
-__global__ void __launch_bounds__(kRoundThreads)
-nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
-          const int *__restrict__ order, int n_max, const int *__restrict__ n_dev, int base,
-          int max_out, float thr,
+constexpr int kTileThreads = 256;
+
+// Phase 1 of a window: one CTA per 64x64 tile of pairwise IoU tests (small CTAs, no shared-memory
+// footprint to speak of, so they share SMs with whatever else is running).
+__global__ void __launch_bounds__(kTileThreads)
+nms_tiles(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea, int n_max,
+          const int *__restrict__ n_dev, int base, float thr,
           unsigned long long *__restrict__ sup,      // [kTriWords] suppressor bitmasks
           unsigned *__restrict__ dead,               // [2*kWin/32]: killed by earlier windows,
                                                      // then "has a suppressor in this window";
                                                      // then [kWin]: which suppressor words of
                                                      // each candidate are non-zero
-          NmsBox *__restrict__ kbox, float *__restrict__ karea,  // kept boxes so far
-          NmsState *__restrict__ st, int *__restrict__ keep, int *__restrict__ n_keep) {
-  extern __shared__ unsigned long long smem_sup[];   // phase 2: [kTriWords]
+          const NmsBox *__restrict__ kbox, const float *__restrict__ karea,  // kept boxes so far
+          const NmsState *__restrict__ st) {
   __shared__ NmsBox jb[64];
   __shared__ float ja[64];
-  __shared__ unsigned long long s_kept[kWords], s_removed[kWords], s_hassup[kWords];
-  __shared__ int s_prefix[kWords + 1];
-  __shared__ int s_last;
-
   if (st->done) return;
-  const unsigned long long t_start = global_ns();
   const int n = n_dev ? min(n_max, __ldg(n_dev)) : n_max;
   const int wcount = max(0, min(kWin, n - base));  // candidates in this window
   const int nb = (wcount + 63) >> 6;               // 64-blocks in this window
@@ -329,7 +326,7 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
   const int tri_tiles = nb * (nb + 1) / 2;
   const int n_tiles = tri_tiles + nb * pb;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kWarps = kRoundThreads / 32;
+  constexpr int kWarps = kTileThreads / 32;
 
   // ---------------- phase 1: IoU tiles ----------------
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -391,17 +388,25 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
     }
   }
 
-  // ---------------- hand-off: the last CTA to finish runs phase 2 ----------------
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(&st->tiles_done, 1u);
-    s_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x == 0) { st->t_ns[0] = t_start; st->t_ns[1] = global_ns(); }
+}
+
+// Phase 2 of a window: one CTA solves the recurrence from the suppressor bitmasks and emits.
+__global__ void __launch_bounds__(kRoundThreads)
+nms_solve(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
+          const int *__restrict__ order, int n_max, const int *__restrict__ n_dev, int base,
+          int max_out, const unsigned long long *__restrict__ sup, unsigned *__restrict__ dead,
+          NmsBox *__restrict__ kbox, float *__restrict__ karea, NmsState *__restrict__ st,
+          int *__restrict__ keep, int *__restrict__ n_keep) {
+  extern __shared__ unsigned long long smem_sup[];   // [64 * nb*(nb+1)/2] suppressor words
+  __shared__ unsigned long long s_kept[kWords], s_removed[kWords], s_hassup[kWords];
+  __shared__ int s_prefix[kWords + 1];
+  if (st->done) return;
+  const unsigned long long t_start = global_ns();
+  const int n = n_dev ? min(n_max, __ldg(n_dev)) : n_max;
+  const int wcount = max(0, min(kWin, n - base));
+  const int n_prev = st->n_kept;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { st->t_ns[0] = t_start; st->t_ns[1] = t_start; }
 
   // ---------------- phase 2: solve the window ----------------
   // only the suppressor words that hold a bit are fetched (at IoU 0.8 that is a few per cent of
@@ -506,17 +511,17 @@ nms_round(const NmsBox *__restrict__ sbox, const float *__restrict__ sarea,
   // reset the per-round scratch for the next window
   for (int w = threadIdx.x; w < 2 * (kWin / 32) + kWin; w += kResolveThreads) dead[w] = 0u;
   __syncthreads();
+  const int total = min(max_out, n_prev + s_prefix[kWords]);
+  // the first window owns the initialisation of the outputs: unused entries of keep are -1
+  if (base == 0)
+    for (int k = total + threadIdx.x; k < max_out; k += kResolveThreads) keep[k] = -1;
   if (threadIdx.x == 0) {
-    const int total = min(max_out, n_prev + s_prefix[kWords]);
+    const bool complete = total >= max_out || base + wcount >= n;
     st->n_kept = total;
-    st->tiles_done = 0u;
     st->t_ns[4] = global_ns();
     n_keep[0] = total;
-    if (total >= max_out || base + wcount >= n) {
-      st->done = 1;
-      n_keep[1] = 1;   // selection complete
-    }
-    __threadfence();
+    if (complete) st->done = 1;
+    if (complete || base == 0) n_keep[1] = complete ? 1 : 0;   // selection complete?
   }
 }
 
@@ -574,15 +579,14 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *
   if (n > 0 && (!boxes || !scores)) return DODT_EINVAL;
   if (reinterpret_cast<uintptr_t>(boxes) % 16 != 0) return DODT_EALIGN;
   cudaStream_t stream = as_stream(stream_);
-  if (!resume) {
-    DODT_CUDA_TRY(cudaMemsetAsync(n_keep, 0, 2 * sizeof(int32_t), stream));
-    if (max_out > 0) DODT_CUDA_TRY(cudaMemsetAsync(keep, 0xFF, sizeof(int32_t) * max_out, stream));
-  }
   if (n == 0 || max_out == 0) {
     // nothing to select: complete. One byte of 0x01 on the zeroed little-endian int32 is 1.
+    DODT_CUDA_TRY(cudaMemsetAsync(n_keep, 0, 2 * sizeof(int32_t), stream));
+    if (max_out > 0) DODT_CUDA_TRY(cudaMemsetAsync(keep, 0xFF, sizeof(int32_t) * max_out, stream));
     DODT_CUDA_TRY(cudaMemsetAsync(n_keep + 1, 1, 1, stream));
     return DODT_OK;
   }
+  // (keep and n_keep are initialised by the first window's solve kernel)
   NmsLayout L;
   nms_layout(n, &L);
   if (!workspace || workspace_bytes < L.total) return DODT_ECAPACITY;
@@ -606,7 +610,7 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *
   const size_t smem = static_cast<size_t>(kTriWords) * sizeof(unsigned long long);
   static bool attr_set = false;  // per process; the attribute is a property of the function
   if (!attr_set) {
-    DODT_CUDA_TRY(cudaFuncSetAttribute(nms_round, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DODT_CUDA_TRY(cudaFuncSetAttribute(nms_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
     attr_set = true;
   }
@@ -632,14 +636,15 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *
       const int wcount = ni - base < kWin ? ni - base : kWin;
       const int nb = (wcount + 63) / 64;
       const int pb = (max_out + 63) / 64;  // upper bound of kept blocks from earlier windows
-      int tiles = nb * (nb + 1) / 2 + (base > 0 ? nb * pb : 0);
-      // the first window gets the whole GPU; later windows usually find the selection complete and
-      // exit, so they are launched narrower (cheaper no-op, still 10 tiles per CTA when they run)
-      const int cap = base == 0 ? 2 * kNumSMs : kNumSMs / 2;
-      const int grid = tiles < cap ? tiles : cap;
-      nms_round<<<grid, kRoundThreads, smem, stream>>>(sbox, sarea, order, ni, n_dev, base, max_out,
-                                                       iou_threshold, sup, dead, kbox, karea, st,
-                                                       keep, n_keep);
+      const int tiles = nb * (nb + 1) / 2 + (base > 0 ? nb * pb : 0);
+      // later windows usually find the selection complete and exit at once: launch them narrower
+      const int cap = base == 0 ? tiles : 2 * kNumSMs;
+      nms_tiles<<<tiles < cap ? tiles : cap, kTileThreads, 0, stream>>>(
+          sbox, sarea, ni, n_dev, base, iou_threshold, sup, dead, kbox, karea, st);
+      DODT_AFTER_LAUNCH();
+      const size_t need = static_cast<size_t>(64) * (nb * (nb + 1) / 2) * sizeof(unsigned long long);
+      nms_solve<<<1, kRoundThreads, need, stream>>>(sbox, sarea, order, ni, n_dev, base, max_out, sup,
+                                                    dead, kbox, karea, st, keep, n_keep);
       DODT_AFTER_LAUNCH();
     }
   }
