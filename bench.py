@@ -80,7 +80,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 16))
+    workers = max(1, min(cores, 64))         # one frame per core (about 1 GB of inputs each)
     steps = max(1, min(args.steps, 6))       # bounded: a CPU frame takes seconds
     warmup = min(args.warmup, 1)
     r = cpu_arm(steps, warmup, workers)
@@ -191,8 +191,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from dodt_b200 import ops
-    from dodt_b200.frontend import FrontEnd
+    from dodt_b200 import ops, shard
+    from dodt_b200.frontend import FrontEnd, HostFrame
     from dodt_b200 import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,32 +209,17 @@ def run_ours(args):
     n_slots = max(2, args.slots)
     slots = [fe.new_slot() for _ in range(n_slots)]
     # one KITTI-tracking-shaped stream per GPU: rank r reads frames of "sequence" r
-    host_inputs = []
-    for i in range(n_slots):
-        inp = synth.frame_inputs(CONFIG_ID, 1000 * rank + i)
-        pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in inp.items()}
-        host_inputs.append(pinned)
-    n_points = host_inputs[0]["points"].shape[1]
-
-    FEATURE_KEYS = ("bev_feat", "img_feat", "bev_1ch", "img_1ch")   # network outputs (GPU-resident in the reference)
-
-    def upload(slot, pinned, skip=()):
-        for k, dst in slot.input_tensors().items():
-            if k in skip:
-                continue
-            src = pinned[k]
-            if k == "points":
-                dst[:, :src.shape[1]].copy_(src, non_blocking=True)
-                slot.n_points = src.shape[1]
-            else:
-                dst.copy_(src, non_blocking=True)
-
-    for s_, p in zip(slots, host_inputs):
-        upload(s_, p)
+    hosts = [HostFrame(fe).fill(synth.frame_inputs(CONFIG_ID, 1000 * rank + i), sequence=rank, frame=i)
+             for i in range(n_slots)]
+    # this shard's detection lists: one fixed-size row block per frame, gathered ONCE at the end
+    block = shard.DetectionBlock(max(args.steps, 1), fe.cfg.avod_nms_size, dev)
+    n_points = hosts[0].n_points
+    for s_, h in zip(slots, hosts):
+        h.upload(s_)
     torch.cuda.synchronize()
     graphs, launches = [], 0
     for i in range(n_slots):
-        g, launches = fe.capture(slots[i], slots[i - 1])
+        g, launches = fe.capture(slots[i], slots[i - 1], block)
         graphs.append(g)
     torch.cuda.synchronize()
 
@@ -273,20 +258,19 @@ def run_ours(args):
             torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gathered = None
+    block.reset()
     barrier()
     w0 = time.time()
     ev0.record()
     replay_round_robin(K)
-    if world > 1:
-        # the only collective of the path: per-shard detection lists
-        last = slots[(K - 1) % n_slots]
-        payload = torch.cat([last.top_idx, last.n_top, last.final_idx, last.n_final])
-        gathered = [torch.empty_like(payload) for _ in range(world)]
-        dist.all_gather(gathered, payload)
+    # the only collective of the path: the shard's detection lists, K frames x 100
+    # rows x 6 floats per rank, inside the timed region
+    gathered = shard.all_gather_blocks(block)
     ev1.record()
     barrier()
     sampler.window = (w0, time.time())
     ms = ev0.elapsed_time(ev1)
+    frames_recorded = min(int(block.cursor.item()), block.rows.shape[0])
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -373,71 +357,67 @@ def run_ours(args):
                 "stage_us": stage_us, "stage_bytes": abytes}
 
     # ------------------------------------------------------------------ e2e: host buffers
+    # Every step: H2D of the frame's inputs from pinned host memory (one packed sensor buffer +
+    # the four feature maps), the frame graph, D2H of the packed results — all on the slot's own
+    # stream, so the copies of one frame overlap the kernels of its neighbours.
     e2e = None
     if not args.no_e2e:
-        copy_stream = torch.cuda.Stream(device=dev)
-        results_host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
-                         for k, v in s_.result_tensors().items()} for s_ in slots]
-        h2d = sum(v.numel() * v.element_size() for v in host_inputs[0].values())
-        d2h = sum(v.numel() * v.element_size() for v in results_host[0].values())
-        Ke = max(6, min(K, 60))
-        done_ev = [None] * n_slots      # graph that last READ slot j (as current or as prev)
-        copied_ev = [None] * n_slots
+        h2d = hosts[0].h2d_bytes
+        d2h = hosts[0].result_buf.numel()
+        done_ev = [None] * n_slots      # graph of slot j finished (it read slots j and j-1)
+        up_ev = [None] * n_slots        # inputs of slot j are on the device
 
-        def e2e_loop(n, skip=()):
+        def e2e_loop(n, features):
+            for st in streams:
+                st.wait_stream(main)
             for i in range(n):
                 j = i % n_slots
-                with torch.cuda.stream(copy_stream):
-                    # slot j was last read by the graph of slot j+1 (as its previous frame), which
-                    # runs after slot j's own graph: wait for it before overwriting the inputs
+                st = streams[j]
+                with torch.cuda.stream(st):
+                    # slot j's inputs were last read by the graph of slot j+1 (as its previous frame)
                     ev = done_ev[(j + 1) % n_slots]
                     if ev is not None:
-                        copy_stream.wait_event(ev)
-                    upload(slots[j], host_inputs[j], skip)
-                    copied_ev[j] = torch.cuda.Event()
-                    copied_ev[j].record(copy_stream)
-                main.wait_event(copied_ev[j])
-                graphs[j].replay()
-                for k, v in slots[j].result_tensors().items():
-                    results_host[j][k].copy_(v, non_blocking=True)
-                done_ev[j] = torch.cuda.Event()
-                done_ev[j].record(main)
+                        st.wait_event(ev)
+                    hosts[j].upload(slots[j], features)
+                    up_ev[j] = torch.cuda.Event()
+                    up_ev[j].record(st)
+                    ev = up_ev[(j - 1) % n_slots]   # this graph reads slot j-1's BEV features
+                    if ev is not None:
+                        st.wait_event(ev)
+                    graphs[j].replay()
+                    done_ev[j] = torch.cuda.Event()
+                    done_ev[j].record(st)
+                    hosts[j].download(slots[j])
+            for st in streams:
+                main.wait_stream(st)
 
-        e2e_loop(n_slots)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(copy_stream):
-            a.record(copy_stream)
-        e2e_loop(Ke)
-        b.record(main)
-        barrier()
-        ems = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": Ke * world / (float(ems.item()) / 1e3), "unit": "frames/s",
+        def timed_e2e(n, features):
+            e2e_loop(n_slots, features)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(main)
+            e2e_loop(n, features)
+            b.record(main)
+            barrier()
+            t_ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            return float(t_ms.item())
+
+        Ke = max(6, min(K, 60))
+        ems = timed_e2e(Ke, True)
+        e2e = {"value": Ke * world / (ems / 1e3), "unit": "frames/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-               "h2d_gbs": h2d * Ke / (float(ems.item()) / 1e3) / 1e9,
+               "h2d_gbs": h2d * Ke / (ems / 1e3) / 1e9,
                "note": "every slot input (points, BEV/image features, RPN head outputs) copied from "
                        "pinned host memory each step; detection lists copied back; PCIe-bound"}
         # the same with the network feature maps left on the device (where the reference has them:
         # they are TF GPU tensors); only sensor data and head outputs cross PCIe
-        Ks = max(6, min(K, 300))
-        e2e_loop(n_slots, FEATURE_KEYS)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(copy_stream):
-            a.record(copy_stream)
-        e2e_loop(Ks, FEATURE_KEYS)
-        b.record(main)
-        barrier()
-        sms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        Ks = max(6, min(K, 600))
+        sms = timed_e2e(Ks, False)
         e2e["sensor_only"] = {
-            "value": Ks * world / (float(sms.item()) / 1e3), "unit": "frames/s", "steps": Ks,
-            "h2d_bytes_per_step": sum(v.numel() * v.element_size() for k, v in host_inputs[0].items()
-                                      if k not in FEATURE_KEYS),
-            "d2h_bytes_per_step": d2h,
+            "value": Ks * world / (sms / 1e3), "unit": "frames/s", "steps": Ks,
+            "h2d_bytes_per_step": hosts[0].sensor_buf.numel(), "d2h_bytes_per_step": d2h,
             "note": "points + RPN/AVOD head outputs from pinned host memory each step; BEV/image "
                     "feature maps resident on the device"}
 
@@ -445,7 +425,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        workers = max(1, min(cores, 16))
+        workers = max(1, min(cores, 64))
         r = cpu_arm(2, 0, workers)
         cpu = {"value": r["fps"], "unit": "frames/s", "cores": workers, "kind": "port",
                "sample": "%d frames of the same workload, one per process; S1/S2 NumPy restatement "
@@ -462,12 +442,16 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "points": n_points, "anchors": fe.num_anchors,
                        "anchors_kept": n_kept, "proposals": n_top,
                        "l2": "inputs %.0f MB/step cycled over %d resident frame slots (> 126 MB L2)"
-                             % (sum(v.numel() * v.element_size() for v in host_inputs[0].values()) / 1e6, n_slots),
+                             % (hosts[0].h2d_bytes / 1e6, n_slots),
                        "parallelism": "one frame stream per GPU, no data-path collective; one "
                                       "all_gather of detection lists per shard"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches * K, "launches_per_step": launches, "clocks": clocks,
             "frame_latency_us_single_stream": frame_latency_us, "streams": n_slots,
+            "gathered": {"ranks": len(gathered), "frames_per_rank": int(block.rows.shape[0]),
+                         "bytes_per_rank": int(block.rows.numel() * 4 + block.counts.numel() * 4
+                                               + block.frame_ids.numel() * 4),
+                         "frames_recorded_rank0": int(frames_recorded)},
         }
         print(json.dumps(line))
     if world > 1:

@@ -74,6 +74,8 @@ SIGNATURES = {
                                  c_void_p]),
     "dodt_gather_rows_multi": (c_int, [POINTER(GatherSpec), c_int32, c_void_p, c_void_p, c_int64,
                                        c_void_p]),
+    "dodt_emit_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "dodt_crop_and_resize_multi": (c_int, [POINTER(CropSpec), c_int32, c_int32, c_void_p, c_int64,
                                            c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "dodt_crop_and_resize": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,

@@ -130,10 +130,58 @@ gather_rows_multi(const GatherMulti g, const int *__restrict__ idx, const int *_
   }
 }
 
+// One frame's detection list appended to the shard-level block that is gathered once per shard
+// (SURVEY 8(e)). The row of the block is taken from a device-side cursor, so the launch is
+// replayable inside a CUDA graph; frames beyond the block's capacity are counted but dropped.
+__global__ void __launch_bounds__(128)
+emit_detections(const float *__restrict__ boxes, const float *__restrict__ scores,
+                const int *__restrict__ keep, const int *__restrict__ n_keep, int max_det,
+                const int *__restrict__ frame_id, float *__restrict__ rows, int *__restrict__ counts,
+                int *__restrict__ frame_ids, int *__restrict__ cursor, int max_frames) {
+  __shared__ int s_row;
+  if (threadIdx.x == 0) s_row = atomicAdd(cursor, 1);
+  __syncthreads();
+  const int row = s_row;
+  if (row >= max_frames) return;
+  const int n = min(max_det, __ldg(n_keep));
+  for (int k = threadIdx.x; k < max_det; k += 128) {
+    float *dst = rows + (static_cast<size_t>(row) * max_det + k) * 6;
+    if (k < n) {
+      const int src = __ldg(keep + k);
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + src);
+      dst[0] = b.x; dst[1] = b.y; dst[2] = b.z; dst[3] = b.w;
+      dst[4] = __ldg(scores + src);
+      dst[5] = static_cast<float>(src);
+    } else {
+      dst[0] = dst[1] = dst[2] = dst[3] = dst[4] = dst[5] = 0.0f;
+    }
+  }
+  if (threadIdx.x == 0) {
+    counts[row] = n;
+    frame_ids[2 * row] = frame_id ? __ldg(frame_id) : -2;
+    frame_ids[2 * row + 1] = frame_id ? __ldg(frame_id + 1) : row;
+  }
+}
+
 }  // namespace
 }  // namespace dodt
 
 extern "C" {
+
+int dodt_emit_detections(const float *boxes, const float *scores, const int32_t *keep,
+                         const int32_t *n_keep, int32_t max_det, const int32_t *frame_id,
+                         float *rows, int32_t *counts, int32_t *frame_ids, int32_t *cursor,
+                         int32_t max_frames, dodt_stream_t stream_) {
+  using namespace dodt;
+  if (!boxes || !scores || !keep || !n_keep || !rows || !counts || !frame_ids || !cursor ||
+      max_det <= 0 || max_frames <= 0)
+    return DODT_EINVAL;
+  if (reinterpret_cast<uintptr_t>(boxes) % 16 != 0) return DODT_EALIGN;
+  emit_detections<<<1, 128, 0, as_stream(stream_)>>>(boxes, scores, keep, n_keep, max_det, frame_id,
+                                                     rows, counts, frame_ids, cursor, max_frames);
+  DODT_AFTER_LAUNCH();
+  return DODT_OK;
+}
 
 int dodt_gather_rows_multi(const dodt_gather_spec *specs, int32_t n_specs, const int32_t *idx,
                            const int32_t *count, int64_t n_max, dodt_stream_t stream_) {

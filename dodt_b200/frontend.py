@@ -51,8 +51,31 @@ class FrontEndConfig:
     nms_max_windows: int = 4                        # launches reserved for the RPN NMS in a graph
 
 
+def _layout(specs, align=256):
+    """[(name, shape, dtype)] -> ({name: (offset, shape, dtype)}, total bytes), 256-byte aligned."""
+    out, off = {}, 0
+    for name, shape, dtype in specs:
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        out[name] = (off, tuple(shape), dtype)
+        off = (off + nbytes + align - 1) // align * align
+    return out, off
+
+
+def _views(buf, layout):
+    views = {}
+    for name, (off, shape, dtype) in layout.items():
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        views[name] = buf[off:off + n].view(dtype).view(shape)
+    return views
+
+
 class FrameSlot:
-    """Device buffers of one in-flight frame: inputs (filled by the caller) and outputs."""
+    """Device buffers of one in-flight frame: inputs (filled by the caller) and outputs.
+
+    The per-frame SENSOR-side inputs (point cloud, RPN / second-stage head outputs) live in one
+    contiguous buffer and the results handed back to the host in another, so that a frame costs
+    one host->device and one device->host copy besides the feature maps (`HostFrame` mirrors the
+    layouts in pinned memory)."""
 
     def __init__(self, fe):
         c, dev = fe.cfg, fe.device
@@ -62,24 +85,30 @@ class FrameSlot:
         nA, C = fe.num_anchors, c.feat_channels
         e = lambda *s, dtype=f32: torch.empty(s, dtype=dtype, device=dev)
         # ---- inputs
-        self.points = e(3, c.max_points)
+        self.sensor_buf = torch.empty(fe.sensor_bytes, dtype=torch.uint8, device=dev)
+        v = _views(self.sensor_buf, fe.sensor_layout)
+        self.points = v["points"]              # (3, max_points)
+        self.rpn_boxes = v["rpn_boxes"]        # regressed BEV boxes [z1,x1,z2,x2] normalised, per anchor
+        self.rpn_img_boxes = v["rpn_img_boxes"]  # regressed image boxes [y1,x1,y2,x2] normalised
+        self.rpn_scores = v["rpn_scores"]
+        self.final_scores = v["final_scores"]
+        self.frame_id = v["frame_id"]          # (sequence, frame) of the frame in this slot
         self.n_points = 0
         self.bev_feat = e(1, H, W, C)
         self.img_feat = e(1, ih, iw, C)
         self.bev_1ch = e(1, H, W, 1)
         self.img_1ch = e(1, ih, iw, 1)
-        self.rpn_boxes = e(nA, 4)          # regressed BEV boxes [z1,x1,z2,x2] normalised, per anchor
-        self.rpn_img_boxes = e(nA, 4)      # regressed image boxes [y1,x1,y2,x2] normalised
-        self.rpn_scores = e(nA)
-        self.final_scores = e(c.rpn_nms_size)
-        # ---- outputs / intermediates
+        # ---- results (one buffer)
+        self.result_buf = torch.empty(fe.result_bytes, dtype=torch.uint8, device=dev)
+        r = _views(self.result_buf, fe.result_layout)
+        self.n_kept, self.n_top, self.n_final = r["n_kept"], r["n_top"], r["n_final"]
+        self.stats, self.top_idx, self.final_idx = r["stats"], r["top_idx"], r["final_idx"]
+        # ---- intermediates
         self.maps = e(c.num_slices + 1, H, W)
         self.occ = e(fe.nx, fe.nz, dtype=torch.uint8)
-        self.stats = e(BEV_STATS_LEN, dtype=i32)
         self.ii = e(fe.nx + 1, fe.nz + 1, dtype=i32)
         self.keep = e(nA, dtype=torch.uint8)
         self.kept_idx = e(nA, dtype=i32)
-        self.n_kept = e(1, dtype=i32)
         self.k_bev_boxes = e(nA, 4)
         self.k_img_boxes = e(nA, 4)
         self.k_rpn_boxes = e(nA, 4)
@@ -87,16 +116,12 @@ class FrameSlot:
         self.k_rpn_scores = e(nA)
         self.rpn_bev_crops = e(nA, c.rpn_crop[0], c.rpn_crop[1], 1)
         self.rpn_img_crops = e(nA, c.rpn_crop[0], c.rpn_crop[1], 1)
-        self.top_idx = e(c.rpn_nms_size, dtype=i32)
-        self.n_top = e(2, dtype=i32)
         self.prop_bev_boxes = e(c.rpn_nms_size, 4)
         self.prop_img_boxes = e(c.rpn_nms_size, 4)
         self.corr = e(1, H, W, fe.corr_channels)
         self.bev_rois = e(c.rpn_nms_size, c.avod_crop[0], c.avod_crop[1], C)
         self.img_rois = e(c.rpn_nms_size, c.avod_crop[0], c.avod_crop[1], C)
         self.corr_rois = e(c.rpn_nms_size, c.avod_crop[0], c.avod_crop[1], fe.corr_channels)
-        self.final_idx = e(c.avod_nms_size, dtype=i32)
-        self.n_final = e(2, dtype=i32)
         # ---- workspaces
         u8 = lambda n: torch.empty(max(int(n), 256), dtype=torch.uint8, device=dev)
         self.ws_bev = u8(ops.bev_workspace_bytes(c.max_points, c.num_slices, fe.nx, fe.nz))
@@ -115,6 +140,57 @@ class FrameSlot:
         """What a step hands back to the host (detection lists; crops stay on the device)."""
         return dict(n_kept=self.n_kept, top_idx=self.top_idx, n_top=self.n_top,
                     final_idx=self.final_idx, n_final=self.n_final, stats=self.stats)
+
+
+FEATURE_KEYS = ("bev_feat", "img_feat", "bev_1ch", "img_1ch")   # network outputs
+
+
+class HostFrame:
+    """Pinned host mirror of one FrameSlot's inputs and results (same packed layouts)."""
+
+    def __init__(self, fe):
+        self.fe = fe
+        self.sensor_buf = torch.empty(fe.sensor_bytes, dtype=torch.uint8).pin_memory()
+        self.sensor = _views(self.sensor_buf, fe.sensor_layout)
+        c = fe.cfg
+        ih, iw = c.image_shape
+        shapes = dict(bev_feat=(1, fe.nz, fe.nx, c.feat_channels), img_feat=(1, ih, iw, c.feat_channels),
+                      bev_1ch=(1, fe.nz, fe.nx, 1), img_1ch=(1, ih, iw, 1))
+        self.features = {k: torch.empty(s, dtype=torch.float32).pin_memory() for k, s in shapes.items()}
+        self.result_buf = torch.empty(fe.result_bytes, dtype=torch.uint8).pin_memory()
+        self.results = _views(self.result_buf, fe.result_layout)
+        self.n_points = 0
+
+    def fill(self, inputs, sequence=0, frame=0):
+        """inputs: dict of NumPy arrays as dodt_b200.synth.frame_inputs returns them."""
+        self.sensor["frame_id"][0] = int(sequence)
+        self.sensor["frame_id"][1] = int(frame)
+        for k, v in inputs.items():
+            t = torch.from_numpy(np.ascontiguousarray(v))
+            if k == "points":
+                self.n_points = t.shape[1]
+                self.sensor["points"][:, :self.n_points].copy_(t)
+            elif k in self.features:
+                self.features[k].copy_(t)
+            else:
+                self.sensor[k].copy_(t)
+        return self
+
+    @property
+    def h2d_bytes(self):
+        return self.sensor_buf.numel() + sum(v.numel() * 4 for v in self.features.values())
+
+    def upload(self, slot, features=True):
+        """Enqueue the host->device copies of this frame on the current stream."""
+        slot.sensor_buf.copy_(self.sensor_buf, non_blocking=True)
+        slot.n_points = self.n_points
+        if features:
+            for k, v in self.features.items():
+                getattr(slot, k).copy_(v, non_blocking=True)
+
+    def download(self, slot):
+        """Enqueue the device->host copy of the frame's results on the current stream."""
+        self.result_buf.copy_(slot.result_buf, non_blocking=True)
 
 
 class FrontEnd:
@@ -140,14 +216,26 @@ class FrontEnd:
                                               c.height_lo, c.height_hi, c.num_slices, True,
                                               c.occ_lo, c.occ_hi)
         self.side_stream = torch.cuda.Stream(device=self.device)
+        f32, i32 = torch.float32, torch.int32
+        nA = self.num_anchors
+        self.sensor_layout, self.sensor_bytes = _layout([
+            ("points", (3, c.max_points), f32), ("rpn_boxes", (nA, 4), f32),
+            ("rpn_img_boxes", (nA, 4), f32), ("rpn_scores", (nA,), f32),
+            ("final_scores", (c.rpn_nms_size,), f32), ("frame_id", (2,), i32)])
+        self.result_layout, self.result_bytes = _layout([
+            ("n_kept", (1,), i32), ("n_top", (2,), i32), ("n_final", (2,), i32),
+            ("stats", (BEV_STATS_LEN,), i32), ("top_idx", (c.rpn_nms_size,), i32),
+            ("final_idx", (c.avod_nms_size,), i32)])
 
     def new_slot(self):
         return FrameSlot(self)
 
     # ---------------------------------------------------------------------------------------
-    def enqueue(self, slot, prev_slot):
+    def enqueue(self, slot, prev_slot, block=None):
         """Enqueue every stage of `slot`'s frame on the current stream (+ the side stream for S4);
         `prev_slot.bev_feat` is frame t of the correlation pair, `slot.bev_feat` frame t+1.
+        block: optional dodt_b200.shard.DetectionBlock on this device — the frame's final
+        detections are appended to it (the list that a sharded run gathers once per shard).
         Capturable into a CUDA graph; returns the number of library kernels launched."""
         c, s = self.cfg, slot
         before = ops.launch_count()
@@ -188,16 +276,19 @@ class FrontEnd:
         # S5b
         ops.nms(s.prop_bev_boxes, s.final_scores, c.avod_nms_size, c.avod_nms_iou,
                 keep=s.final_idx, n_keep=s.n_final, workspace=s.ws_nms_final, n_dev=s.n_top)
+        if block is not None:
+            ops.emit_detections(s.prop_bev_boxes, s.final_scores, s.final_idx, s.n_final, block,
+                                frame_id=s.frame_id)
         return ops.launch_count() - before
 
-    def capture(self, slot, prev_slot):
+    def capture(self, slot, prev_slot, block=None):
         """Warm up eagerly once (sets kernel attributes), then capture `enqueue` into a graph.
         Returns (graph, kernels per replay)."""
-        self.enqueue(slot, prev_slot)
+        self.enqueue(slot, prev_slot, block)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            launches = self.enqueue(slot, prev_slot)
+            launches = self.enqueue(slot, prev_slot, block)
         return graph, launches
 
     # ---------------------------------------------------------------------------------------

@@ -213,6 +213,20 @@ def gather_rows_multi(pairs, idx, count):
                                         _stream()), "dodt_gather_rows_multi")
 
 
+def emit_detections(boxes, scores, keep, n_keep, block, frame_id=None):
+    """Append keep[:n_keep[0]] of one frame to a dodt_b200.shard.DetectionBlock living on the device
+    (rows = box, score, index). frame_id: optional device int32 [2] (sequence, frame)."""
+    _need_cuda(boxes, scores, keep, n_keep, block.rows, block.counts, block.frame_ids, block.cursor,
+               frame_id)
+    max_frames, max_det = int(block.rows.shape[0]), int(block.rows.shape[1])
+    if keep.numel() < max_det:
+        raise ValueError("keep holds fewer than max_det entries")
+    check(load().dodt_emit_detections(_ptr(boxes), _ptr(scores), _ptr(keep), _ptr(n_keep), max_det,
+                                      _ptr(frame_id), _ptr(block.rows), _ptr(block.counts),
+                                      _ptr(block.frame_ids), _ptr(block.cursor), max_frames, _stream()),
+          "dodt_emit_detections")
+
+
 def crop_and_resize_multi(triples, crop_size, extrapolation_value=0.0, n_dev=None, box_ind=None):
     """One launch for several (image [B,H,W,C], boxes [n,4], out [n,ch,cw,C]) triples that share
     the box count, box_ind (None = zeros) and crop size."""

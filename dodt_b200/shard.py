@@ -78,6 +78,14 @@ class DetectionBlock:
         self.rows = torch.zeros((max_frames, max_det, DET_COLS), dtype=torch.float32, device=device)
         self.counts = torch.zeros((max_frames,), dtype=torch.int32, device=device)
         self.frame_ids = torch.full((max_frames, 2), -1, dtype=torch.int32, device=device)
+        self.cursor = torch.zeros((1,), dtype=torch.int32, device=device)   # device-side row cursor
+        self.n = 0
+
+    def reset(self):
+        """Forget every stored frame (device-side cursor included); no synchronisation."""
+        self.frame_ids.fill_(-1)
+        self.counts.zero_()
+        self.cursor.zero_()
         self.n = 0
 
     def append(self, sequence, frame, boxes, scores, indices, count):
@@ -99,19 +107,23 @@ class DetectionBlock:
         self.n += 1
 
 
-def gather_detections(block, group=None):
-    """all_gather of every rank's DetectionBlock. Returns {(sequence, frame): rows [count, DET_COLS]}
-    on every rank (host tensors). With no process group it just unpacks the local block."""
-    parts = [(block.rows, block.counts, block.frame_ids)]
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        world = dist.get_world_size(group)
-        parts = []
-        gathered = []
-        for t in (block.rows, block.counts, block.frame_ids):
-            bufs = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(bufs, t.contiguous(), group=group)
-            gathered.append(bufs)
-        parts = list(zip(*gathered))
+def all_gather_blocks(block, group=None):
+    """The ONE collective of a shard: all_gather of every rank's block (rows, counts, frame ids).
+    Returns [(rows, counts, frame_ids)] per rank, on the block's device, without synchronising;
+    with no process group (or a world of one) it is the local block."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return [(block.rows, block.counts, block.frame_ids)]
+    world = dist.get_world_size(group)
+    gathered = []
+    for t in (block.rows, block.counts, block.frame_ids):
+        bufs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(bufs, t.contiguous(), group=group)
+        gathered.append(bufs)
+    return list(zip(*gathered))
+
+
+def unpack_blocks(parts):
+    """[(rows, counts, frame_ids)] -> {(sequence, frame): rows [count, DET_COLS]} (host tensors)."""
     out = {}
     for rows, counts, ids in parts:
         rows, counts, ids = rows.cpu(), counts.cpu(), ids.cpu()
@@ -124,3 +136,8 @@ def gather_detections(block, group=None):
                 raise RuntimeError("frame %r was processed by two ranks" % (key,))
             out[key] = rows[i, :int(counts[i])].clone()
     return out
+
+
+def gather_detections(block, group=None):
+    """all_gather of every rank's DetectionBlock, unpacked: {(sequence, frame): rows} on every rank."""
+    return unpack_blocks(all_gather_blocks(block, group))

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DODT_FE_VERSION 101 /* major*100 + minor */
+#define DODT_FE_VERSION 102 /* major*100 + minor */
 
 typedef void *dodt_stream_t; /* cudaStream_t */
 
@@ -162,6 +162,18 @@ typedef struct dodt_gather_spec {
 int dodt_gather_rows_multi(const dodt_gather_spec *specs /* host */, int32_t n_specs,
                            const int32_t *idx, const int32_t *count, int64_t n_max,
                            dodt_stream_t stream);
+
+/* Multi-GPU hand-off (the per-frame rows the reference writes with np.savetxt,
+ * avod/core/dt_evaluator.py:1098-1147, and that a sharded run gathers once per shard): appends the
+ * detections keep[0 .. *n_keep) of one frame to a block of fixed-size lists.
+ * rows [max_frames, max_det, 6] f32 = box (4), score, index into boxes; counts [max_frames];
+ * frame_ids [max_frames, 2] = the two int32 at frame_id (sequence, frame; NULL: -2, row);
+ * cursor: device int32, the next free row (incremented by the call; rows past max_frames are
+ * dropped, the cursor keeps counting). All device pointers; graph-capturable. */
+int dodt_emit_detections(const float *boxes, const float *scores, const int32_t *keep,
+                         const int32_t *n_keep, int32_t max_det, const int32_t *frame_id,
+                         float *rows, int32_t *counts, int32_t *frame_ids, int32_t *cursor,
+                         int32_t max_frames, dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * S3 — tf.image.crop_and_resize (TensorFlow 1.3.0 core/kernels/crop_and_resize_op.cc, bilinear),

@@ -69,7 +69,14 @@ def run_frame(inp, prev_bev_feat, rpn_nms=(1024, 0.8), avod_nms=(100, 0.01), tim
 
 
 def _worker(args):
+    """One frame in one process. BLAS is held to one thread per process: the pool already uses
+    every core, and np.dot inside get_point_filter would otherwise oversubscribe them."""
     config, frame = args
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
     inp = frame_inputs(config, frame)
     prev, _ = s.feature_pair(config, frame + 1)
     t0 = time.perf_counter()

@@ -111,3 +111,47 @@ def test_nms_device_count_and_window_cap(lib):
     keep, n_keep = ops.nms(b, s, 50, 0.3, max_windows=1)        # 50 found inside the first window
     assert n_keep.cpu().tolist() == [50, 1]
     np.testing.assert_array_equal(keep.cpu().numpy(), want[:50])
+
+
+def test_host_frame_and_detection_block(lib):
+    """HostFrame (packed pinned inputs/results) drives a graph-captured frame whose final detections
+    are appended to a shard DetectionBlock by dodt_emit_detections; the unpacked block equals the
+    oracle's final NMS selection (box, score, index), frame after frame, and overflow is dropped."""
+    from dodt_b200 import shard, synth
+    from dodt_b200.frontend import FrontEnd, HostFrame
+    from oracle import cpu_frontend
+    fe = FrontEnd()
+    slots = [fe.new_slot(), fe.new_slot()]
+    inputs = [synth.frame_inputs(2, 50), synth.frame_inputs(2, 51)]
+    hosts = [HostFrame(fe).fill(inp, sequence=3, frame=50 + i) for i, inp in enumerate(inputs)]
+    for h, s in zip(hosts, slots):
+        h.upload(s)
+    block = shard.DetectionBlock(3, fe.cfg.avod_nms_size, fe.device)
+    graph, _ = fe.capture(slots[1], slots[0], block)
+    block.reset()
+    graph.replay()
+    hosts[1].download(slots[1])
+    torch.cuda.synchronize()
+    ref = cpu_frontend.run_frame(inputs[1], inputs[0]["bev_feat"])
+    _check(slots[1], ref)
+    got = shard.gather_detections(block)
+    assert list(got) == [(3, 51)]
+    rows = got[(3, 51)].numpy()
+    kept = ref["kept"]
+    prop = inputs[1]["rpn_boxes"][kept][ref["top"]]
+    np.testing.assert_array_equal(rows[:, 5].astype(np.int64), ref["final"])
+    np.testing.assert_array_equal(rows[:, :4], prop[ref["final"]])
+    np.testing.assert_array_equal(rows[:, 4], inputs[1]["final_scores"][ref["final"]])
+    # packed results on the host
+    res = hosts[1].results
+    assert res["n_final"].tolist() == [len(ref["final"]), 1]
+    np.testing.assert_array_equal(res["final_idx"][:len(ref["final"])].numpy(), ref["final"])
+    assert int(res["n_kept"][0]) == len(kept)
+    # a second frame through the same graph lands in the next row; capacity overflow is dropped
+    hosts[1].fill(inputs[1], sequence=3, frame=52).upload(slots[1])
+    for _ in range(4):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert int(block.cursor.item()) == 5
+    ids = block.frame_ids.cpu().numpy()
+    assert ids.tolist() == [[3, 51], [3, 52], [3, 52]]
