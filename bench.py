@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slots", type=int, default=4)
+    ap.add_argument("--slots", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -331,7 +331,8 @@ def run_ours(args):
         "S5_rpn_nms": lambda s, p: ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx,
                                            n_keep=s.n_top, workspace=s.ws_nms_rpn, n_dev=s.n_kept, max_windows=c.nms_max_windows),
         "S4_correlation": lambda s, p: ops.correlation(p.bev_feat, s.bev_feat, 1, c.corr_max_displacement, 1,
-                                                       c.corr_stride_2, c.corr_padding, out=s.corr),
+                                                       c.corr_stride_2, c.corr_padding, out=s.corr,
+                                                       max_ctas=c.corr_max_ctas),
         "S3_avod_crops": lambda s, p: ops.crop_and_resize_multi([(s.bev_feat, s.prop_bev_boxes, s.bev_rois),
                                                                  (s.img_feat, s.prop_img_boxes, s.img_rois),
                                                                  (s.corr, s.prop_bev_boxes, s.corr_rois)],
@@ -340,6 +341,9 @@ def run_ours(args):
                                              n_keep=s.n_final, workspace=s.ws_nms_final, n_dev=s.n_top),
     }
     stage_us = {k: time_stage(f) for k, f in stage_fns.items()}
+    # the same kernel when it has the GPU to itself (two CTAs per SM instead of the runner's one)
+    corr_alone_us = time_stage(lambda s, p: ops.correlation(p.bev_feat, s.bev_feat, 1, c.corr_max_displacement,
+                                                            1, c.corr_stride_2, c.corr_padding, out=s.corr))
     n_kept = int(slots[0].n_kept.item())
     n_top = int(slots[0].n_top[0].item())
     abytes = fe.algorithmic_bytes(n_points, n_kept, n_top)
@@ -351,6 +355,11 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes["S4"],
+                "launch": "as the frame runner launches it: %d persistent CTAs (one per SM), the rest "
+                          "of each SM left to the other stages of neighbouring frames" % c.corr_max_ctas,
+                "standalone": {"us": corr_alone_us, "achieved": abytes["S4"] / (corr_alone_us * 1e-6) / 1e9,
+                               "frac": abytes["S4"] / (corr_alone_us * 1e-6) / 1e9 / peak,
+                               "launch": "296 CTAs (two per SM), nothing else running"},
                 "frame": {"algorithmic_bytes": abytes["total"],
                           "achieved": abytes["total"] * fps / world / 1e9,
                           "frac": abytes["total"] * fps / world / 1e9 / peak},

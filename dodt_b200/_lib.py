@@ -85,6 +85,9 @@ SIGNATURES = {
                                            c_int32, POINTER(c_int32)]),
     "dodt_correlation": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "dodt_correlation_shared": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                        c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
+                                        c_void_p]),
     "dodt_nms_workspace_bytes": (c_size_t, [c_int64]),
     "dodt_nms_state_offset": (c_size_t, [c_int64]),
     "dodt_nms": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_float, c_int32, c_int32,

@@ -30,7 +30,7 @@ namespace dodt {
 
 // correlation_tma.cu: TMA-pipelined persistent kernel; returns 1 when it does not apply
 int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, int r, int out_h,
-                    int out_w, int shift, float *out, cudaStream_t stream);
+                    int out_w, int shift, float *out, int max_ctas, cudaStream_t stream);
 
 namespace {
 
@@ -273,7 +273,16 @@ int dodt_correlation(const float *a, const float *b, int32_t batch, int32_t heig
                      int32_t channels, int32_t kernel_size, int32_t max_displacement,
                      int32_t stride_1, int32_t stride_2, int32_t pad, float *out,
                      dodt_stream_t stream_) {
+  return dodt_correlation_shared(a, b, batch, height, width, channels, kernel_size, max_displacement,
+                                 stride_1, stride_2, pad, out, 0, stream_);
+}
+
+int dodt_correlation_shared(const float *a, const float *b, int32_t batch, int32_t height,
+                            int32_t width, int32_t channels, int32_t kernel_size,
+                            int32_t max_displacement, int32_t stride_1, int32_t stride_2,
+                            int32_t pad, float *out, int32_t max_ctas, dodt_stream_t stream_) {
   using namespace dodt;
+  if (max_ctas < 0) return DODT_EINVAL;
   if (!a || !b || !out) return DODT_EINVAL;
   CorrGeom g;
   const int rc = fill_geom(batch, height, width, channels, kernel_size, max_displacement, stride_1,
@@ -286,7 +295,7 @@ int dodt_correlation(const float *a, const float *b, int32_t batch, int32_t heig
   // undefined there; here such taps are zero.
   if (g.ks == 1 && g.s1 == 1 && g.s2 == 2 && aligned) {
     const int done = correlation_tma(a, b, g.batch, g.H, g.W, g.C, g.r, g.out_h, g.out_w,
-                                     g.md - g.pad, out, stream);
+                                     g.md - g.pad, out, max_ctas, stream);
     if (done <= 0) return done;
   }
   if (g.ks == 1 && g.s1 == 1 && g.s2 == 2 && channels % kCC == 0 && aligned && g.batch <= 65535) {

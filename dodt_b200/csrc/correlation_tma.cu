@@ -519,7 +519,7 @@ int launch(const float *a, const float *b, int N, int H, int W, int C, int out_h
 
 template <int R, int PX, int FRONT, int TH = kTH, int CTAS = 1>
 int launch_async(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w,
-                 int shift, float *out, cudaStream_t stream) {
+                 int shift, float *out, int max_ctas, cudaStream_t stream) {
   using Cfg = TmaCfg<R, TH>;
   constexpr int kThr = kTW / (2 * PX) * 2 * TH;
   static bool attr_set = false;
@@ -535,7 +535,8 @@ int launch_async(const float *a, const float *b, int N, int H, int W, int C, int
   g.n_tiles = g.tiles_x * g.tiles_y * N;
   g.pow2 = (C & (C - 1)) == 0 ? 1 : 0;
   g.inv_c = 1.0f / static_cast<float>(C);
-  const int grid = g.n_tiles < CTAS * kNumSMs ? g.n_tiles : CTAS * kNumSMs;
+  int grid = g.n_tiles < CTAS * kNumSMs ? g.n_tiles : CTAS * kNumSMs;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;   // persistent CTAs: any count works
   corr_async_k1<R, PX, FRONT, TH, CTAS><<<grid, kThr, Cfg::SMEM_BYTES, stream>>>(a, b, g, out);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
@@ -546,7 +547,7 @@ int launch_async(const float *a, const float *b, int N, int H, int W, int C, int
 // returns DODT_OK if launched, 1 if this path does not apply, DODT_E* on failure.
 // impl: 0 = cp.async pipeline (default), 1 = tensor-TMA pipeline (kept for A/B measurements)
 int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, int r, int out_h,
-                    int out_w, int shift, float *out, cudaStream_t stream) {
+                    int out_w, int shift, float *out, int max_ctas, cudaStream_t stream) {
   if (C % kCC != 0 || reinterpret_cast<uintptr_t>(a) % 16 || reinterpret_cast<uintptr_t>(b) % 16)
     return 1;
   if (static_cast<long long>(out_h) * out_w < 1024) return 1;  // tiny maps: tiles mostly padding
@@ -564,30 +565,30 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
   }
   if (impl == 2) {   // 16 warps x 2 pixels per thread
     switch (r) {
-      case 1: return launch_async<1, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
-      case 2: return launch_async<2, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      case 1: return launch_async<1, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+      case 2: return launch_async<2, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
       default: return 1;
     }
   }
   if (impl == 3) {   // next unit's copies issued in the first half of the unit (A/B timing: slower)
     switch (r) {
-      case 1: return launch_async<1, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
-      case 2: return launch_async<2, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      case 1: return launch_async<1, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+      case 2: return launch_async<2, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
       default: return 1;
     }
   }
   if (impl == 4) {   // 16-row tiles, 8 warps, one CTA per SM (A/B timing: 68 us vs 59 us)
     switch (r) {
-      case 1: return launch_async<1, 4, 0>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
-      case 2: return launch_async<2, 4, 0>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+      case 1: return launch_async<1, 4, 0>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+      case 2: return launch_async<2, 4, 0>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
       default: return 1;
     }
   }
   // default: 8-row tiles, 4 warps per CTA, TWO CTAs per SM — the per-unit barrier, the exposed
   // tail of the copies and the epilogue of one CTA hide behind the other CTA's math
   switch (r) {
-    case 1: return launch_async<1, 4, 0, 8, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
-    case 2: return launch_async<2, 4, 0, 8, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
+    case 1: return launch_async<1, 4, 0, 8, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+    case 2: return launch_async<2, 4, 0, 8, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
     default: return 1;
   }
 }

@@ -49,6 +49,8 @@ class FrontEndConfig:
     corr_padding: int = 5
     corr_stride_2: int = 2
     nms_max_windows: int = 4                        # launches reserved for the RPN NMS in a graph
+    corr_max_ctas: int = 148                        # one persistent correlation CTA per SM: the
+                                                    # other half of each SM runs neighbouring frames
 
 
 def _layout(specs, align=256):
@@ -244,7 +246,7 @@ class FrontEnd:
         self.side_stream.wait_stream(main)
         with torch.cuda.stream(self.side_stream):
             ops.correlation(prev_slot.bev_feat, s.bev_feat, 1, c.corr_max_displacement, 1,
-                            c.corr_stride_2, c.corr_padding, out=s.corr)
+                            c.corr_stride_2, c.corr_padding, out=s.corr, max_ctas=c.corr_max_ctas)
         # S1
         ops.bev_slices(s.points[:, :s.n_points], self.bev_params, s.maps, s.occ, s.stats, s.ws_bev)
         # S2

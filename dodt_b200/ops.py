@@ -309,7 +309,9 @@ def correlation_out_shape(H, W, kernel_size, max_displacement, stride_1, stride_
     return int(hwc[0]), int(hwc[1]), int(hwc[2])
 
 
-def correlation(a, b, kernel_size, max_displacement, stride_1, stride_2, pad, out=None):
+def correlation(a, b, kernel_size, max_displacement, stride_1, stride_2, pad, out=None,
+                max_ctas=0):
+    """max_ctas > 0: cap on the persistent CTAs of the launch (dodt_correlation_shared)."""
     _need_cuda(a, b, out)
     if a.dim() != 4:
         raise ValueError("input_a must have rank 4")
@@ -327,9 +329,9 @@ def correlation(a, b, kernel_size, max_displacement, stride_1, stride_2, pad, ou
     oh, ow, oc = correlation_out_shape(H, W, kernel_size, max_displacement, stride_1, stride_2, pad)
     if out is None:
         out = torch.empty((N, oh, ow, oc), dtype=torch.float32, device=a.device)
-    check(load().dodt_correlation(_ptr(a), _ptr(b), N, H, W, C, kernel_size, max_displacement,
-                                  stride_1, stride_2, pad, _ptr(out), _stream()),
-          "dodt_correlation")
+    check(load().dodt_correlation_shared(_ptr(a), _ptr(b), N, H, W, C, kernel_size,
+                                         max_displacement, stride_1, stride_2, pad, _ptr(out),
+                                         int(max_ctas), _stream()), "dodt_correlation")
     return out
 
 

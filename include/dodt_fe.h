@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DODT_FE_VERSION 102 /* major*100 + minor */
+#define DODT_FE_VERSION 103 /* major*100 + minor */
 
 typedef void *dodt_stream_t; /* cudaStream_t */
 
@@ -218,6 +218,14 @@ int dodt_correlation(const float *a, const float *b, int32_t batch, int32_t heig
                      int32_t channels, int32_t kernel_size, int32_t max_displacement,
                      int32_t stride_1, int32_t stride_2, int32_t pad, float *out,
                      dodt_stream_t stream);
+/* The same, for a caller that runs other work next to it: max_ctas > 0 caps the number of
+ * (persistent) CTAs of the launch, e.g. one per SM instead of two, which leaves half of every SM's
+ * registers and shared memory to kernels of other streams (the frame-stream runner overlaps the
+ * latency-bound stages of neighbouring frames with the correlation this way). 0 = no cap. */
+int dodt_correlation_shared(const float *a, const float *b, int32_t batch, int32_t height,
+                            int32_t width, int32_t channels, int32_t kernel_size,
+                            int32_t max_displacement, int32_t stride_1, int32_t stride_2,
+                            int32_t pad, float *out, int32_t max_ctas, dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * S5 — tf.image.non_max_suppression (TensorFlow 1.3.0 core/kernels/non_max_suppression_op.cc),
