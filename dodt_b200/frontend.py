@@ -233,64 +233,67 @@ class FrontEnd:
         return FrameSlot(self)
 
     # ---------------------------------------------------------------------------------------
-    def enqueue(self, slot, prev_slot, block=None):
+    def enqueue(self, slot, prev_slot, block=None, skip=()):
         """Enqueue every stage of `slot`'s frame on the current stream (+ the side stream for S4);
         `prev_slot.bev_feat` is frame t of the correlation pair, `slot.bev_feat` frame t+1.
         block: optional dodt_b200.shard.DetectionBlock on this device — the frame's final
         detections are appended to it (the list that a sharded run gathers once per shard).
+        skip: stage names left out (profiling only: "S1", "S2", "S3a", "S5a", "S4", "S3b", "S5b").
         Capturable into a CUDA graph; returns the number of library kernels launched."""
         c, s = self.cfg, slot
         before = ops.launch_count()
         main = torch.cuda.current_stream()
         # S4 on the side stream (independent of the point cloud)
         self.side_stream.wait_stream(main)
-        with torch.cuda.stream(self.side_stream):
-            ops.correlation(prev_slot.bev_feat, s.bev_feat, 1, c.corr_max_displacement, 1,
-                            c.corr_stride_2, c.corr_padding, out=s.corr, max_ctas=c.corr_max_ctas)
-        # S1
-        ops.bev_slices(s.points[:, :s.n_points], self.bev_params, s.maps, s.occ, s.stats, s.ws_bev)
-        # S2
-        ops.integral_image_2d(s.occ, s.ii, s.ws_ii)
-        ops.anchor_filter_2d(self.anchors, s.ii, self.nx, self.nz, self.min_x, self.min_z,
-                             c.voxel_size, c.density_threshold, keep=s.keep)
-        ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact)
-        ops.gather_rows_multi([(self.anchor_bev_boxes, s.k_bev_boxes),
-                               (self.anchor_img_boxes, s.k_img_boxes),
-                               (s.rpn_boxes, s.k_rpn_boxes),
-                               (s.rpn_img_boxes, s.k_rpn_img_boxes),
-                               (s.rpn_scores, s.k_rpn_scores)], s.kept_idx, s.n_kept)
-        # S3a
-        ops.crop_and_resize_multi([(s.bev_1ch, s.k_bev_boxes, s.rpn_bev_crops),
-                                   (s.img_1ch, s.k_img_boxes, s.rpn_img_crops)],
-                                  c.rpn_crop, 0.0, n_dev=s.n_kept)
-        # S5a
-        ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx,
-                n_keep=s.n_top, workspace=s.ws_nms_rpn, n_dev=s.n_kept,
-                max_windows=c.nms_max_windows)
-        ops.gather_rows_multi([(s.k_rpn_boxes, s.prop_bev_boxes),
-                               (s.k_rpn_img_boxes, s.prop_img_boxes)], s.top_idx, s.n_top)
+        if "S4" not in skip:
+            with torch.cuda.stream(self.side_stream):
+                ops.correlation(prev_slot.bev_feat, s.bev_feat, 1, c.corr_max_displacement, 1,
+                                c.corr_stride_2, c.corr_padding, out=s.corr, max_ctas=c.corr_max_ctas)
+        if "S1" not in skip:
+            ops.bev_slices(s.points[:, :s.n_points], self.bev_params, s.maps, s.occ, s.stats, s.ws_bev)
+        if "S2" not in skip:
+            ops.integral_image_2d(s.occ, s.ii, s.ws_ii)
+            ops.anchor_filter_2d(self.anchors, s.ii, self.nx, self.nz, self.min_x, self.min_z,
+                                 c.voxel_size, c.density_threshold, keep=s.keep)
+            ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact)
+            ops.gather_rows_multi([(self.anchor_bev_boxes, s.k_bev_boxes),
+                                   (self.anchor_img_boxes, s.k_img_boxes),
+                                   (s.rpn_boxes, s.k_rpn_boxes),
+                                   (s.rpn_img_boxes, s.k_rpn_img_boxes),
+                                   (s.rpn_scores, s.k_rpn_scores)], s.kept_idx, s.n_kept)
+        if "S3a" not in skip:
+            ops.crop_and_resize_multi([(s.bev_1ch, s.k_bev_boxes, s.rpn_bev_crops),
+                                       (s.img_1ch, s.k_img_boxes, s.rpn_img_crops)],
+                                      c.rpn_crop, 0.0, n_dev=s.n_kept)
+        if "S5a" not in skip:
+            ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx,
+                    n_keep=s.n_top, workspace=s.ws_nms_rpn, n_dev=s.n_kept,
+                    max_windows=c.nms_max_windows)
+            ops.gather_rows_multi([(s.k_rpn_boxes, s.prop_bev_boxes),
+                                   (s.k_rpn_img_boxes, s.prop_img_boxes)], s.top_idx, s.n_top)
         # S3b (the corr crop needs S4)
         main.wait_stream(self.side_stream)
-        ops.crop_and_resize_multi([(s.bev_feat, s.prop_bev_boxes, s.bev_rois),
-                                   (s.img_feat, s.prop_img_boxes, s.img_rois),
-                                   (s.corr, s.prop_bev_boxes, s.corr_rois)],
-                                  c.avod_crop, 0.0, n_dev=s.n_top)
-        # S5b
-        ops.nms(s.prop_bev_boxes, s.final_scores, c.avod_nms_size, c.avod_nms_iou,
-                keep=s.final_idx, n_keep=s.n_final, workspace=s.ws_nms_final, n_dev=s.n_top)
+        if "S3b" not in skip:
+            ops.crop_and_resize_multi([(s.bev_feat, s.prop_bev_boxes, s.bev_rois),
+                                       (s.img_feat, s.prop_img_boxes, s.img_rois),
+                                       (s.corr, s.prop_bev_boxes, s.corr_rois)],
+                                      c.avod_crop, 0.0, n_dev=s.n_top)
+        if "S5b" not in skip:
+            ops.nms(s.prop_bev_boxes, s.final_scores, c.avod_nms_size, c.avod_nms_iou,
+                    keep=s.final_idx, n_keep=s.n_final, workspace=s.ws_nms_final, n_dev=s.n_top)
         if block is not None:
             ops.emit_detections(s.prop_bev_boxes, s.final_scores, s.final_idx, s.n_final, block,
                                 frame_id=s.frame_id)
         return ops.launch_count() - before
 
-    def capture(self, slot, prev_slot, block=None):
+    def capture(self, slot, prev_slot, block=None, skip=()):
         """Warm up eagerly once (sets kernel attributes), then capture `enqueue` into a graph.
         Returns (graph, kernels per replay)."""
         self.enqueue(slot, prev_slot, block)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            launches = self.enqueue(slot, prev_slot, block)
+            launches = self.enqueue(slot, prev_slot, block, skip)
         return graph, launches
 
     # ---------------------------------------------------------------------------------------

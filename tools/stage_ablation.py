@@ -1,0 +1,52 @@
+"""Throughput of the multi-stream frame pipeline with one stage left out at a time: the marginal
+cost of each stage in frames/s terms (device-resident inputs, as bench.py's `value`).
+usage: python tools/stage_ablation.py [slots] [steps]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dodt_b200 import synth  # noqa: E402
+from dodt_b200.frontend import FrontEnd, HostFrame  # noqa: E402
+
+n_slots = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
+fe = FrontEnd()
+slots = [fe.new_slot() for _ in range(n_slots)]
+for i, s in enumerate(slots):
+    HostFrame(fe).fill(synth.frame_inputs(2, i)).upload(s)
+torch.cuda.synchronize()
+streams = [torch.cuda.Stream() for _ in range(n_slots)]
+main = torch.cuda.current_stream()
+
+
+def run(skip):
+    graphs = [fe.capture(slots[i], slots[i - 1], None, skip)[0] for i in range(n_slots)]
+
+    def rr(n):
+        for st in streams:
+            st.wait_stream(main)
+        for i in range(n):
+            with torch.cuda.stream(streams[i % n_slots]):
+                graphs[i % n_slots].replay()
+        for st in streams:
+            main.wait_stream(st)
+    rr(3 * n_slots)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    rr(steps)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / steps
+
+
+base = run(())
+print("all stages: %.1f us/frame (%.0f frames/s)" % (base, 1e6 / base))
+for st in ("S1", "S2", "S3a", "S5a", "S4", "S3b", "S5b"):
+    t = run((st,))
+    print("without %-3s: %6.1f us/frame  (stage costs %5.1f us of throughput)" % (st, t, base - t))
+t = run(("S1", "S2", "S3a", "S5a", "S3b", "S5b"))
+print("only S4    : %6.1f us/frame" % t)
+t = run(("S4",))
