@@ -19,16 +19,19 @@
 //            the S+2 slice predicates in fp64 (bit-exact with NumPy), then for every map the point
 //            belongs to a warp-aggregated atomicMax of an inverted (y-bin, point index) key (height
 //            maps) or a warp-aggregated atomicAdd (density counts) on the map cell itself, and a
-//            byte store into the occupancy grid. The lane whose atomic found the cell empty appends
-//            the cell to a "touched" list (block-aggregated through shared memory).
-//   pass 2  bev_resolve                       — walks only the touched cells (a few thousand on a
-//            real frame), gathers the winning point, evaluates dist_to_plane / normalisation in
-//            fp64 in NumPy's operation order and overwrites the key with the final float; density
-//            counts go through a host-computed LUT of min(1, ln(n+1)/ln16) so they are bit-exact
-//            with NumPy's log. The 0/1-point slice fallback of bev_slices.py:76-99 is applied here.
+//            byte store into the occupancy grid. Every atomic is fire-and-forget (RED): nothing
+//            waits for an L2 round trip, a warp retires as soon as its reductions are issued.
+//   pass 2  bev_resolve_scan                  — streams over the maps (uint4 loads); for every
+//            non-empty cell it gathers the winning point, evaluates dist_to_plane / normalisation
+//            in fp64 in NumPy's operation order and overwrites the key with the final float;
+//            density counts go through a host-computed LUT of min(1, ln(n+1)/ln16) so they are
+//            bit-exact with NumPy's log. The 0/1-point slice fallback of bev_slices.py:76-99 is
+//            applied here. (An earlier version collected first-touch cells in a list so that this
+//            pass visited only those; the returning atomics it needed serialised two L2 round
+//            trips per point and cost more than re-reading the 13 MB of maps.)
 //
-// HBM traffic per frame is therefore the algorithmic minimum: 12 B (fp32) per point read once
-// plus one write of the maps; keys and counts never exist outside the maps.
+// HBM traffic per frame: 12 B (fp32) per point, one write and one read of the maps; keys and
+// counts never exist outside the maps.
 #include <math.h>
 #include <string.h>
 
@@ -109,12 +112,8 @@ __device__ __forceinline__ int voxel_bin(double v, double voxel) {
   return __double2int_rd(__ddiv_rn(v, voxel));
 }
 
-// Shared staging of first-touch cells so that a block issues ONE atomicAdd on the global list
-// counter instead of one per warp.
 struct BlockStage {
-  unsigned count;
-  unsigned base;
-  int slice_pts[DODT_MAX_SLICES + 2];
+  int slice_pts[DODT_MAX_SLICES + 2];   // points per slice seen by this block
 };
 
 template <typename T, int VEC>
@@ -122,13 +121,10 @@ __global__ void __launch_bounds__(kBlock)
 bev_accumulate(const T *__restrict__ px, const T *__restrict__ py, const T *__restrict__ pz,
                long long n, int vec_ok, const __grid_constant__ BevDev P,
                unsigned *__restrict__ maps, unsigned char *__restrict__ occ,
-               int *__restrict__ stats, unsigned *__restrict__ touched) {
-  constexpr int kStageCap = kBlock * VEC * 2;
+               int *__restrict__ stats) {
   __shared__ BlockStage st;
-  __shared__ unsigned stage[kStageCap];
 
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) { st.count = 0; st.base = 0; }
   if (threadIdx.x < DODT_MAX_SLICES + 2) st.slice_pts[threadIdx.x] = 0;
   __syncthreads();
 
@@ -209,91 +205,118 @@ bev_accumulate(const T *__restrict__ px, const T *__restrict__ py, const T *__re
         }
         continue;
       }
-      bool first = false;
-      unsigned e = 0;
       if (in_m) {
-        e = static_cast<unsigned>(m) * HW + cell;
+        const unsigned e = static_cast<unsigned>(m) * HW + cell;
         const unsigned peers = __match_any_sync(active, e);
         const bool leader = lane == __ffs(peers) - 1;
         if (m < P.S) {
           const unsigned best = __reduce_max_sync(peers, inv_key);
-          if (leader) first = atomicMax(&maps[e], best) == 0u;
+          if (leader) atomicMax(&maps[e], best);                                   // RED.MAX
         } else {
-          if (leader) first = atomicAdd(&maps[e], static_cast<unsigned>(__popc(peers))) == 0u;
-        }
-      }
-      if (first) {
-        const unsigned slot = atomicAdd(&st.count, 1u);
-        if (slot < kStageCap) {
-          stage[slot] = e;
-        } else {  // staging full (a point in >2 maps everywhere): append directly
-          const unsigned g = atomicAdd(reinterpret_cast<unsigned *>(&stats[DODT_BEV_STAT_TOUCHED]), 1u);
-          if (g < P.touched_cap) touched[g] = e; else stats[DODT_BEV_STAT_OVERFLOW] = 1;
+          if (leader) atomicAdd(&maps[e], static_cast<unsigned>(__popc(peers)));   // RED.ADD
         }
       }
     }
   }
 
   __syncthreads();
-  const unsigned staged = st.count < kStageCap ? st.count : kStageCap;
-  if (threadIdx.x == 0 && staged)
-    st.base = atomicAdd(reinterpret_cast<unsigned *>(&stats[DODT_BEV_STAT_TOUCHED]), staged);
   if (threadIdx.x < n_pred && st.slice_pts[threadIdx.x]) {
     const int m = threadIdx.x;
     const int slot = m < P.S ? m : (m == P.S ? DODT_BEV_STAT_DENSITY : DODT_BEV_STAT_OCC);
     atomicAdd(&stats[slot], st.slice_pts[m]);
   }
-  __syncthreads();
-  for (unsigned k = threadIdx.x; k < staged; k += kBlock) {
-    const unsigned g = st.base + k;
-    if (g < P.touched_cap) touched[g] = stage[k]; else stats[DODT_BEV_STAT_OVERFLOW] = 1;
-  }
 }
 
+// one map entry: key / count -> final float (see the file header)
 template <typename T>
-__global__ void __launch_bounds__(kBlock)
-bev_resolve(const T *__restrict__ px, const T *__restrict__ py, const T *__restrict__ pz,
-            const __grid_constant__ BevDev P, unsigned *__restrict__ maps,
-            const int *__restrict__ stats, const unsigned *__restrict__ touched,
-            int *__restrict__ winner_idx, int *__restrict__ counts) {
-  const int HW = P.nx * P.nz;
-  unsigned nt = static_cast<unsigned>(stats[DODT_BEV_STAT_TOUCHED]);
-  if (nt > P.touched_cap) nt = P.touched_cap;
-  const unsigned stride = gridDim.x * kBlock;
-  for (unsigned k = blockIdx.x * kBlock + threadIdx.x; k < nt; k += stride) {
-    const unsigned e = touched[k];
-    const int m = e / HW;
-    const int cell = e - m * HW;
-    const unsigned raw = maps[e];
-    if (m < P.S) {
-      if (P.filter_mode && stats[m] <= 1) {
-        // bev_slices.py:76-99: a slice with 0 or 1 points is replaced by one origin point
-        if (cell != P.origin_cell) maps[e] = 0u;
-        continue;
-      }
-      const unsigned key = 0xFFFFFFFFu - raw;
-      const unsigned idx = key & P.idx_mask;
-      const double xd = static_cast<double>(__ldg(px + idx));
-      const double yd = static_cast<double>(__ldg(py + idx));
-      const double zd = static_cast<double>(__ldg(pz + idx));
-      double h;
-      if (P.height_from_y) {
-        h = yd;  // voxel_grid_2d.py:105-106 (no ground plane)
-      } else {
-        // dist_to_plane, geometry_utils.py:40: ((a*x + b*y) + c*z + d) / sqrt(a^2+b^2+c^2)
-        h = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.a, xd), __dmul_rn(P.b, yd)),
-                                __dmul_rn(P.c, zd)), P.d);
-        h = __ddiv_rn(h, P.norm);
-      }
-      // bev_slices.py:107-109: (height - slice_lo) / height_per_division
-      const double v = __ddiv_rn(__dsub_rn(h, P.lo[m]), P.hpd);
-      maps[e] = __float_as_uint(__double2float_rn(v));
-      if (winner_idx) winner_idx[e] = static_cast<int>(idx);
+__device__ __forceinline__ unsigned resolve_entry(const T *__restrict__ px, const T *__restrict__ py,
+                                                  const T *__restrict__ pz, const BevDev &P,
+                                                  const int *__restrict__ stats, unsigned raw, int m,
+                                                  int cell, unsigned e, int *__restrict__ winner_idx,
+                                                  int *__restrict__ counts) {
+  if (m < P.S) {
+    if (P.filter_mode && stats[m] <= 1) {
+      // bev_slices.py:76-99: a slice with 0 or 1 points is replaced by one origin point
+      return cell == P.origin_cell ? __float_as_uint(P.origin_val[m]) : 0u;
+    }
+    const unsigned key = 0xFFFFFFFFu - raw;
+    const unsigned idx = key & P.idx_mask;
+    const double xd = static_cast<double>(__ldg(px + idx));
+    const double yd = static_cast<double>(__ldg(py + idx));
+    const double zd = static_cast<double>(__ldg(pz + idx));
+    double h;
+    if (P.height_from_y) {
+      h = yd;  // voxel_grid_2d.py:105-106 (no ground plane)
     } else {
-      // bev_generator.py:34-35: min(1, log(n + 1) / norm) through the host LUT
-      const float v = raw < static_cast<unsigned>(P.lut_len) ? P.lut[raw] : 1.0f;
-      maps[e] = __float_as_uint(v);
-      if (counts) counts[cell] = static_cast<int>(raw);
+      // dist_to_plane, geometry_utils.py:40: ((a*x + b*y) + c*z + d) / sqrt(a^2+b^2+c^2)
+      h = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.a, xd), __dmul_rn(P.b, yd)),
+                              __dmul_rn(P.c, zd)), P.d);
+      h = __ddiv_rn(h, P.norm);
+    }
+    // bev_slices.py:107-109: (height - slice_lo) / height_per_division
+    const double v = __ddiv_rn(__dsub_rn(h, P.lo[m]), P.hpd);
+    if (winner_idx) winner_idx[e] = static_cast<int>(idx);
+    return __float_as_uint(__double2float_rn(v));
+  }
+  // bev_generator.py:34-35: min(1, log(n + 1) / norm) through the host LUT
+  if (counts) counts[cell] = static_cast<int>(raw);
+  return __float_as_uint(raw < static_cast<unsigned>(P.lut_len) ? P.lut[raw] : 1.0f);
+}
+
+// VEC = 4 (nx*nz a multiple of 4; uint4 loads): the maps are ~93 % zeros, so each warp first
+// sweeps its entries and queues the non-empty ones in shared memory, then resolves the queue with
+// all 32 lanes busy — the fp64 evaluation is not executed once per sparse hit with 31 lanes idle.
+// VEC = 1: plain entry-per-thread scan for odd grid sizes.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock)
+bev_resolve_scan(const T *__restrict__ px, const T *__restrict__ py, const T *__restrict__ pz,
+                 const __grid_constant__ BevDev P, unsigned *__restrict__ maps,
+                 const int *__restrict__ stats, int *__restrict__ winner_idx,
+                 int *__restrict__ counts) {
+  const int HW = P.nx * P.nz;
+  const unsigned total = static_cast<unsigned>(HW) * (P.S + 1);
+  if (VEC == 4) {
+    constexpr int kQueue = 32 + 4 * 32;
+    __shared__ uint2 queue[kBlock / 32][kQueue];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint2 *q = queue[warp];
+    int qn = 0;                                              // warp-uniform
+    auto drain = [&](int first, int count) {                 // resolve q[first .. first+count)
+      if (lane < count) {
+        const uint2 it = q[first + lane];
+        const int m = it.x / HW;
+        maps[it.x] = resolve_entry<T>(px, py, pz, P, stats, it.y, m, it.x - m * HW, it.x, winner_idx, counts);
+      }
+    };
+    const unsigned warp_span = 32 * 4;
+    const unsigned stride = gridDim.x * (kBlock / 32) * warp_span;
+    for (unsigned base = (blockIdx.x * (kBlock / 32) + warp) * warp_span; base < total; base += stride) {
+      const unsigned e0 = base + lane * 4;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (e0 < total) v = *reinterpret_cast<const uint4 *>(maps + e0);
+      const unsigned raw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool nz = raw[k] != 0u;
+        const unsigned mask = __ballot_sync(0xffffffffu, nz);
+        if (nz) q[qn + __popc(mask & ((1u << lane) - 1u))] = make_uint2(e0 + k, raw[k]);
+        qn += __popc(mask);
+      }
+      __syncwarp();
+      while (qn >= 32) {
+        qn -= 32;
+        drain(qn, 32);
+        __syncwarp();
+      }
+    }
+    drain(0, qn);
+  } else {
+    const unsigned stride = gridDim.x * kBlock;
+    for (unsigned e = blockIdx.x * kBlock + threadIdx.x; e < total; e += stride) {
+      const unsigned raw = maps[e];
+      if (raw == 0u) continue;
+      const int m = e / HW;
+      maps[e] = resolve_entry<T>(px, py, pz, P, stats, raw, m, e - m * HW, e, winner_idx, counts);
     }
   }
   if (blockIdx.x == 0 && P.filter_mode && threadIdx.x < P.S && P.origin_cell >= 0) {
@@ -325,11 +348,7 @@ int dodt_bev_grid(const double extents[6], double voxel_size, int32_t grid[6]) {
 
 size_t dodt_bev_workspace_bytes(int64_t n_points, int32_t num_slices, int32_t nx, int32_t nz) {
   if (n_points < 0 || num_slices < 0 || nx <= 0 || nz <= 0) return 0;
-  // touched list: one uint32 per (map, cell) first touch
-  const uint64_t by_points = static_cast<uint64_t>(n_points) * (num_slices + 1);
-  const uint64_t by_cells = static_cast<uint64_t>(num_slices + 1) * nx * nz;
-  const uint64_t cap = by_points < by_cells ? by_points : by_cells;
-  return static_cast<size_t>((cap + 64) * sizeof(uint32_t));
+  return 256;   // no scratch is needed any more (keys and counts live in the maps); kept in the ABI
 }
 
 int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, int64_t row_stride,
@@ -413,10 +432,8 @@ int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, int64_t row_s
       P.origin_val[s] = static_cast<float>(v);
     }
   }
-  const size_t need = dodt_bev_workspace_bytes(n, S, P.nx, P.nz);
-  if (!workspace || workspace_bytes < need) return DODT_ECAPACITY;
-  unsigned *touched = static_cast<unsigned *>(workspace);
-  P.touched_cap = static_cast<unsigned>(need / sizeof(uint32_t));
+  (void)workspace;
+  (void)workspace_bytes;
 
   DODT_CUDA_TRY(cudaMemsetAsync(maps, 0, sizeof(float) * HW * (S + 1), stream));
   DODT_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(int32_t) * DODT_BEV_STATS_LEN, stream));
@@ -428,7 +445,7 @@ int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, int64_t row_s
   }
 
   unsigned *umaps = reinterpret_cast<unsigned *>(maps);
-  const int resolve_blocks = 2 * kNumSMs;
+  const int resolve_blocks = 8 * kNumSMs;
   if (pts_dtype == DODT_F32) {
     const float *px = static_cast<const float *>(pts);
     const float *py = px + row_stride, *pz = px + 2 * row_stride;
@@ -440,12 +457,15 @@ int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, int64_t row_s
       const int vec_ok = (reinterpret_cast<uintptr_t>(px) % 16 == 0 && row_stride % 4 == 0) ? 1 : 0;
       const int blocks = ceil_div(n, static_cast<int64_t>(kBlock) * vec);
       if (dense)
-        bev_accumulate<float, 4><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, vec_ok, P, umaps, occ, stats, touched);
+        bev_accumulate<float, 4><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, vec_ok, P, umaps, occ, stats);
       else
-        bev_accumulate<float, 1><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, 1, P, umaps, occ, stats, touched);
+        bev_accumulate<float, 1><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, 1, P, umaps, occ, stats);
       DODT_AFTER_LAUNCH();
     }
-    bev_resolve<float><<<resolve_blocks, kBlock, 0, stream>>>(px, py, pz, P, umaps, stats, touched, winner_idx, counts);
+    if (HW % 4 == 0)
+      bev_resolve_scan<float, 4><<<resolve_blocks, kBlock, 0, stream>>>(px, py, pz, P, umaps, stats, winner_idx, counts);
+    else
+      bev_resolve_scan<float, 1><<<resolve_blocks, kBlock, 0, stream>>>(px, py, pz, P, umaps, stats, winner_idx, counts);
     DODT_AFTER_LAUNCH();
   } else {
     const double *px = static_cast<const double *>(pts);
@@ -456,12 +476,15 @@ int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, int64_t row_s
       const int vec_ok = (reinterpret_cast<uintptr_t>(px) % 16 == 0 && row_stride % 2 == 0) ? 1 : 0;
       const int blocks = ceil_div(n, static_cast<int64_t>(kBlock) * vec);
       if (dense)
-        bev_accumulate<double, 2><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, vec_ok, P, umaps, occ, stats, touched);
+        bev_accumulate<double, 2><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, vec_ok, P, umaps, occ, stats);
       else
-        bev_accumulate<double, 1><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, 1, P, umaps, occ, stats, touched);
+        bev_accumulate<double, 1><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, 1, P, umaps, occ, stats);
       DODT_AFTER_LAUNCH();
     }
-    bev_resolve<double><<<resolve_blocks, kBlock, 0, stream>>>(px, py, pz, P, umaps, stats, touched, winner_idx, counts);
+    if (HW % 4 == 0)
+      bev_resolve_scan<double, 4><<<resolve_blocks, kBlock, 0, stream>>>(px, py, pz, P, umaps, stats, winner_idx, counts);
+    else
+      bev_resolve_scan<double, 1><<<resolve_blocks, kBlock, 0, stream>>>(px, py, pz, P, umaps, stats, winner_idx, counts);
     DODT_AFTER_LAUNCH();
   }
   return DODT_OK;
