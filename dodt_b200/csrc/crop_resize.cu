@@ -154,24 +154,40 @@ __device__ __forceinline__ void crop_tables_body(const CropMulti &m, int s,
   const int nr = min(R, n_eff - roi0);
   const float4 *boxes = reinterpret_cast<const float4 *>(m.boxes[s]);
 
-  // ---- phase 1: axis tables
-  for (int e = threadIdx.x; e < nr * axes; e += kCropThreads) {
-    const int rl = e / axes, a = e - rl * axes;
+  // ---- phase 1: axis tables, one thread per (ROI, axis): the scale (one fp32 division) is
+  // computed once and the crop positions of the axis are walked in a loop
+  for (int t = threadIdx.x; t < nr * 2; t += kCropThreads) {
+    const int rl = t >> 1;
+    const bool is_y = (t & 1) == 0;
     const float4 box = __ldg(boxes + roi0 + rl);  // y1, x1, y2, x2
-    const bool is_y = a < ch;
-    int i0 = 0, i1 = 0;
-    float lerp = 0.0f;
-    const bool ok = is_y ? sample_coord(box.x, box.z, H, ch, a, &i0, &i1, &lerp)
-                         : sample_coord(box.y, box.w, W, cw, a - ch, &i0, &i1, &lerp);
-    int flag = ok ? 1 : 0;
-    int base = 0;
+    const float lo = is_y ? box.x : box.y, hi = is_y ? box.z : box.w;
+    const int size = is_y ? H : W, crop = is_y ? ch : cw;
+    const int stride = is_y ? W * C : C;
+    int base = 0, bad = 0;
     if (is_y) {
       const int b_in = box_ind ? __ldg(box_ind + roi0 + rl) : 0;
-      if (b_in < 0 || b_in >= m.batch) flag = -1;   // TF leaves such rows untouched
+      if (b_in < 0 || b_in >= m.batch) bad = 1;   // TF leaves such rows untouched
       else base = b_in * H * W * C;
     }
-    const int stride = is_y ? W * C : C;
-    tab[e] = make_int4(base + i0 * stride, base + i1 * stride, __float_as_int(lerp), flag);
+    int4 *row = tab + rl * axes + (is_y ? 0 : ch);
+    const float sm1 = static_cast<float>(size - 1);
+    if (crop > 1) {
+      const float scale = __fdiv_rn(__fmul_rn(__fsub_rn(hi, lo), sm1), static_cast<float>(crop - 1));
+      const float start = __fmul_rn(lo, sm1);
+      for (int i = 0; i < crop; ++i) {
+        const float in = __fadd_rn(start, __fmul_rn(static_cast<float>(i), scale));
+        const bool ok = !(in < 0.0f || in > sm1);
+        const float f = floorf(in);
+        const int i0 = ok ? static_cast<int>(f) : 0, i1 = ok ? static_cast<int>(ceilf(in)) : 0;
+        row[i] = make_int4(base + i0 * stride, base + i1 * stride, __float_as_int(__fsub_rn(in, f)),
+                           bad ? -1 : (ok ? 1 : 0));
+      }
+    } else {
+      int i0 = 0, i1 = 0;
+      float lerp = 0.0f;
+      const bool ok = sample_coord(lo, hi, size, 1, 0, &i0, &i1, &lerp);
+      row[0] = make_int4(base + i0 * stride, base + i1 * stride, __float_as_int(lerp), bad ? -1 : (ok ? 1 : 0));
+    }
   }
   __syncthreads();
 
