@@ -478,3 +478,33 @@ def test_nms_special_scores_and_device_count(dd):
         want = O.non_max_suppression(boxes[:cut], scores[:cut], 1500, 0.6)
         assert n_keep.cpu().tolist() == [len(want), 1], cut
         np.testing.assert_array_equal(keep[:len(want)].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_bev_and_filter_adversarial_random_configs(dd, seed):
+    """Randomised configurations (voxel size, slice count and range, extents, point dtype) with
+    clouds built to sit on every rounding edge: points snapped to voxel multiples, to slice
+    boundaries +- one ulp, to the open extents, duplicates, and points outside. S1 maps, winner
+    indices, counts and occupancy must equal the oracle bit for bit; the S2 keep mask on random
+    (partly out-of-range, partly negative) anchors likewise."""
+    from dodt_b200 import synth
+    from adversarial import adversarial_case
+    rng = np.random.default_rng(1900 + seed)
+    pc, voxel, ext, lo, hi, S = adversarial_case(seed)
+    buf, ref, cfg = _run_bev(dd, pc, voxel=voxel, extents=ext, lo=lo, hi=hi, S=S)
+    _check_bev(buf, ref, S)
+    pc64 = np.asarray(pc, dtype=np.float64)
+    try:
+        occ, vox = O.occupancy_grid(pc64, synth.GROUND_PLANE, ext, voxel)
+    except IndexError:
+        return                                                    # no point in the 0.2-2.0 m slice
+    np.testing.assert_array_equal(buf.occ.cpu().numpy(), occ)
+    a = np.stack([rng.uniform(ext[0][0] - 6, ext[0][1] + 6, 4000), np.zeros(4000),
+                  rng.uniform(ext[2][0] - 6, ext[2][1] + 6, 4000), rng.uniform(0.05, 6.0, 4000),
+                  np.ones(4000), rng.uniform(0.05, 6.0, 4000)], 1)
+    if seed % 3 == 0:
+        a = a.astype(np.float32)
+    grid = dd.VoxelGrid2D.from_occupancy(buf.occ, voxel, ext)
+    for thr in (1, 2):
+        np.testing.assert_array_equal(dd.get_empty_anchor_filter_2d(a, grid, thr),
+                                      O.empty_anchor_filter_2d(a, occ, voxel, vox["min_coord"][[0, 2]], thr))

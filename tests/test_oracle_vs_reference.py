@@ -11,6 +11,8 @@ from dodt_b200 import synth as S
 from oracle import np_oracle as O
 from oracle import ref_shim
 
+S_GROUND = S.GROUND_PLANE
+
 pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
 
 
@@ -45,6 +47,37 @@ def test_bev_slices_live_other_config():
     got = O.bev_slices(pc, plane, ext, 0.25, 0.0, 1.5, 3)
     for a, b in zip(ref['height_maps'] + [ref['density_map']], got['height_maps'] + [got['density_map']]):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_adversarial_configs_live(seed):
+    """The edge-case clouds of tests/adversarial.py (voxel edges, slice boundaries +- ulp, open
+    extents, duplicates; random voxel size / slices / extents): oracle == live reference, so the
+    GPU test that compares against the oracle on the same cases is pinned to the reference."""
+    from adversarial import adversarial_case
+    from avod.core import anchor_filter
+    pc, voxel, ext, lo, hi, S = adversarial_case(seed)
+    pc = np.asarray(pc, dtype=np.float64)     # the reference pipeline hands float64
+    gen = ref_shim.reference_bev_slices(lo, hi, S)
+    ref = gen.generate_bev('lidar', pc, S_GROUND, ext, voxel)
+    got = O.bev_slices(pc, S_GROUND, ext, voxel, lo, hi, S)
+    for a, b in zip(ref['height_maps'] + [ref['density_map']], got['height_maps'] + [got['density_map']]):
+        np.testing.assert_array_equal(a, b)
+    try:
+        vg = ref_shim.reference_sliced_voxel_grid_2d(pc, S_GROUND, ext, voxel)
+    except IndexError:
+        with pytest.raises(IndexError):
+            O.occupancy_grid(pc, S_GROUND, ext, voxel)
+        return
+    occ, vox = O.occupancy_grid(pc, S_GROUND, ext, voxel)
+    np.testing.assert_array_equal(np.squeeze(vg.leaf_layout_2d, 1) + 1, occ)
+    rng = np.random.default_rng(1900 + seed)
+    a = np.stack([rng.uniform(ext[0][0] - 6, ext[0][1] + 6, 4000), np.zeros(4000),
+                  rng.uniform(ext[2][0] - 6, ext[2][1] + 6, 4000), rng.uniform(0.05, 6.0, 4000),
+                  np.ones(4000), rng.uniform(0.05, 6.0, 4000)], 1)
+    for thr in (1, 2):
+        np.testing.assert_array_equal(O.empty_anchor_filter_2d(a, occ, voxel, vox["min_coord"][[0, 2]], thr),
+                                      anchor_filter.get_empty_anchor_filter_2d(a, vg, thr))
 
 
 @pytest.mark.parametrize("seed,n,thr", [(0, 20000, 1), (4, 5000, 1), (5, 40000, 3)])
