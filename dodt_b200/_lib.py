@@ -74,6 +74,14 @@ SIGNATURES = {
                                  c_void_p]),
     "dodt_gather_rows_multi": (c_int, [POINTER(GatherSpec), c_int32, c_void_p, c_void_p, c_int64,
                                        c_void_p]),
+    "dodt_grid_anchor_shape": (c_int, [POINTER(c_double), POINTER(c_double), c_int32, POINTER(c_int32)]),
+    "dodt_grid_anchors": (c_int, [POINTER(c_double), POINTER(c_double), c_int32, POINTER(c_double),
+                                  POINTER(c_double), c_void_p, c_void_p]),
+    "dodt_project_to_bev": (c_int, [c_void_p, c_int32, c_int64, POINTER(c_double), c_int32, c_void_p,
+                                    c_void_p, c_void_p]),
+    "dodt_project_to_image_space": (c_int, [c_void_p, c_int32, c_int64, POINTER(c_double), c_int32,
+                                            c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "dodt_offset_to_anchor": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
     "dodt_emit_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "dodt_crop_and_resize_multi": (c_int, [POINTER(CropSpec), c_int32, c_int32, c_void_p, c_int64,

@@ -213,6 +213,77 @@ def gather_rows_multi(pairs, idx, count):
                                         _stream()), "dodt_gather_rows_multi")
 
 
+# ------------------------------------------------------------------------------------------ anchors
+
+
+def _dbl(values, n):
+    arr = np.asarray(values, dtype=np.float64).reshape(-1)
+    if arr.shape != (n,):
+        raise ValueError("expected %d values, got shape %r" % (n, np.shape(values)))
+    return (ctypes.c_double * n)(*[float(v) for v in arr])
+
+
+def grid_anchor_shape(area_extents, anchor_stride, n_sizes):
+    """(nz, nx, n_sizes, 2) of avod grid_anchor_3d_generator.tile_anchors_3d."""
+    shape = (ctypes.c_int32 * 4)()
+    check(load().dodt_grid_anchor_shape(_dbl(area_extents, 6), _dbl(anchor_stride, 2), int(n_sizes), shape),
+          "dodt_grid_anchor_shape")
+    return tuple(int(v) for v in shape)
+
+
+def grid_anchors(area_extents, anchor_3d_sizes, anchor_stride, ground_plane, device=None):
+    """box_3d_to_anchor(tile_anchors_3d(...)) as a CUDA float64 [N, 6] tensor."""
+    sizes = np.asarray(anchor_3d_sizes, dtype=np.float64).reshape(-1, 3)
+    nz, nx, ns, nr = grid_anchor_shape(area_extents, anchor_stride, len(sizes))
+    out = torch.empty((nz * nx * ns * nr, 6), dtype=torch.float64, device=device or "cuda")
+    check(load().dodt_grid_anchors(_dbl(area_extents, 6), _dbl(sizes, 3 * len(sizes)), len(sizes),
+                                   _dbl(anchor_stride, 2), _dbl(ground_plane, 4), _ptr(out), _stream()),
+          "dodt_grid_anchors")
+    return out
+
+
+def _anchors_arg(anchors):
+    _need_cuda(anchors)
+    if anchors.dim() != 2 or anchors.shape[1] != 6:
+        raise TypeError("Given input does not have valid number of attributes. "
+                        "Should be N x 6 for anchor.")
+    return anchors.contiguous()
+
+
+def project_to_bev(anchors, bev_extents, tf_order=False, want_metres=False):
+    """anchors [n, 6] f32/f64 CUDA -> normalised corners float32 [n, 4] (and corners in metres)."""
+    a = _anchors_arg(anchors)
+    n = a.shape[0]
+    norm = torch.empty((n, 4), dtype=torch.float32, device=a.device)
+    metres = torch.empty((n, 4), dtype=torch.float32, device=a.device) if want_metres else None
+    check(load().dodt_project_to_bev(_ptr(a), _dtype_code(a), n, _dbl(bev_extents, 4), int(bool(tf_order)),
+                                     _ptr(norm), _ptr(metres), _stream()), "dodt_project_to_bev")
+    return (metres, norm) if want_metres else norm
+
+
+def project_to_image_space(anchors, stereo_calib_p2, image_shape, tf_order=False, want_pixels=False):
+    a = _anchors_arg(anchors)
+    n = a.shape[0]
+    norm = torch.empty((n, 4), dtype=torch.float32, device=a.device)
+    pixels = torch.empty((n, 4), dtype=torch.float32, device=a.device) if want_pixels else None
+    check(load().dodt_project_to_image_space(_ptr(a), _dtype_code(a), n, _dbl(stereo_calib_p2, 12),
+                                             int(image_shape[0]), int(image_shape[1]),
+                                             int(bool(tf_order)), _ptr(norm), _ptr(pixels), _stream()),
+          "dodt_project_to_image_space")
+    return (pixels, norm) if want_pixels else norm
+
+
+def offset_to_anchor(anchors, offsets):
+    a = _anchors_arg(anchors)
+    o = _anchors_arg(offsets)
+    if a.shape != o.shape:
+        raise ValueError("anchors and offsets must have the same shape")
+    out = torch.empty((a.shape[0], 6), dtype=torch.float64, device=a.device)
+    check(load().dodt_offset_to_anchor(_ptr(a), _dtype_code(a), _ptr(o), _dtype_code(o), a.shape[0],
+                                       _ptr(out), _stream()), "dodt_offset_to_anchor")
+    return out
+
+
 def emit_detections(boxes, scores, keep, n_keep, block, frame_id=None):
     """Append keep[:n_keep[0]] of one frame to a dodt_b200.shard.DetectionBlock living on the device
     (rows = box, score, index). frame_id: optional device int32 [2] (sequence, frame)."""

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DODT_FE_VERSION 103 /* major*100 + minor */
+#define DODT_FE_VERSION 104 /* major*100 + minor */
 
 typedef void *dodt_stream_t; /* cudaStream_t */
 
@@ -162,6 +162,39 @@ typedef struct dodt_gather_spec {
 int dodt_gather_rows_multi(const dodt_gather_spec *specs /* host */, int32_t n_specs,
                            const int32_t *idx, const int32_t *count, int64_t n_max,
                            dodt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Anchor geometry between the stages — host NumPy in the reference.
+ * ---------------------------------------------------------------------------------------- */
+/* shape[4] = {nz, nx, n_sizes, 2 rotations} of the anchor grid that
+ * avod/core/anchor_generators/grid_anchor_3d_generator.py:39-108 (tile_anchors_3d) tiles over
+ * extents (x_min,x_max,y_min,y_max,z_min,z_max) with stride (x, z); the grid has their product
+ * anchors, ordered z row (far to near), x column, size, rotation. Host only. */
+int dodt_grid_anchor_shape(const double extents[6], const double stride[2], int32_t n_sizes,
+                           int32_t shape[4]);
+/* anchors: out device float64 [N, 6] = box_3d_to_anchor(tile_anchors_3d(...))
+ * (avod/core/box_3d_encoder.py:85-132), bit-identical to NumPy. sizes: host [n_sizes, 3] (l, w, h),
+ * n_sizes <= 16; plane: host a, b, c, d with b != 0. */
+int dodt_grid_anchors(const double extents[6], const double *sizes, int32_t n_sizes,
+                      const double stride[2], const double plane[4], double *anchors,
+                      dodt_stream_t stream);
+/* avod/core/anchor_projector.py:13-69 (project_to_bev). anchors [n, 6] of dtype; bev_extents
+ * x_min, x_max, z_min, z_max (host); outputs float32 [n, 4] (either may be NULL): corners
+ * normalised by the extent ranges, and in metres from the top-left of the map. tf_order = 0:
+ * [x1, z1, x2, z2] as the reference returns them; 1: [z1, x1, z2, x2], the order
+ * tf.image.crop_and_resize wants (anchor_projector.py:254-273 reorder_projected_boxes). */
+int dodt_project_to_bev(const void *anchors, int32_t dtype, int64_t n, const double bev_extents[4],
+                        int32_t tf_order, float *boxes_norm, float *boxes_metres,
+                        dodt_stream_t stream);
+/* avod/core/anchor_projector.py:72-156 (project_to_image_space): min / max of the eight cuboid
+ * corners projected with the 3x4 camera matrix p2 (host, row-major); outputs float32 [n, 4]
+ * [x1, y1, x2, y2] (tf_order: [y1, x1, y2, x2]) normalised by the image size, and in pixels. */
+int dodt_project_to_image_space(const void *anchors, int32_t dtype, int64_t n, const double p2[12],
+                                int32_t image_h, int32_t image_w, int32_t tf_order,
+                                float *boxes_norm, float *boxes_pixels, dodt_stream_t stream);
+/* avod/core/anchor_encoder.py:99-150 (offset_to_anchor): out float64 [n, 6]. */
+int dodt_offset_to_anchor(const void *anchors, int32_t anchors_dtype, const void *offsets,
+                          int32_t offsets_dtype, int64_t n, double *out, dodt_stream_t stream);
 
 /* Multi-GPU hand-off (the per-frame rows the reference writes with np.savetxt,
  * avod/core/dt_evaluator.py:1098-1147, and that a sharded run gathers once per shard): appends the

@@ -60,7 +60,7 @@ def test_struct_layouts_match_header(lib, tmp_path):
 
 def test_host_only_entry_points(lib):
     from dodt_b200 import _lib, ops
-    assert lib.dodt_version() == 103
+    assert lib.dodt_version() == 104
     assert lib.dodt_strerror(0).decode().lower().startswith("ok") or lib.dodt_strerror(0)
     for code in (_lib.DODT_EINVAL, _lib.DODT_ESHAPE, _lib.DODT_ECAPACITY, _lib.DODT_ECUDA, _lib.DODT_EALIGN):
         assert len(lib.dodt_strerror(code)) > 0
@@ -140,3 +140,17 @@ def test_missing_library_fails_loudly(tmp_path):
             % (ROOT, str(tmp_path / "nope.so")))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout
     assert "RAISED True" in out
+
+
+def test_grid_anchor_shape_matches_reference_arange(lib):
+    """Host-only: (nz, nx, sizes, rotations) == the np.arange lengths of
+    avod/core/anchor_generators/grid_anchor_3d_generator.py:62-72, including the degenerate areas
+    of grid_anchor_3d_generator_test.py:32-70."""
+    from dodt_b200 import anchors as A
+    from dodt_b200 import ops, synth
+    assert ops.grid_anchor_shape(synth.AREA_EXTENTS, synth.ANCHOR_STRIDE, 2) == (140, 160, 2, 2)
+    for ext, stride in (([(-1., 1.), (-1., 0.), (0., 1.)], [1, 1]), ([(0., 0.), (-1., 0.), (0., 2.)], [1, 1]),
+                        ([(-1., 1.), (-1., 0.), (0., 0.)], [1, 1]), ([(-3.3, 7.1), (-1, 0), (0.2, 9.9)], [0.7, 0.3])):
+        boxes = A.tile_anchors_3d(ext, [[1., 1., 1.], [2., 1., 1.]], stride, [0., -1., 0., 0.])
+        nz, nx, ns, nr = ops.grid_anchor_shape(ext, stride, 2)
+        assert nz * nx * ns * nr == len(boxes), (ext, stride)
