@@ -322,9 +322,9 @@ def run_ours(args):
                                    ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact),
                                    ops.gather_rows_multi([(fe.anchor_bev_boxes, s.k_bev_boxes),
                                                           (fe.anchor_img_boxes, s.k_img_boxes),
-                                                          (s.rpn_boxes, s.k_rpn_boxes),
-                                                          (s.rpn_img_boxes, s.k_rpn_img_boxes),
-                                                          (s.rpn_scores, s.k_rpn_scores)], s.kept_idx, s.n_kept)),
+                                                          (s.rpn_scores, s.k_rpn_scores)], s.kept_idx, s.n_kept),
+                                   ops.rpn_decode(fe.anchors, s.rpn_offsets, s.kept_idx, s.n_kept, fe.bev_extents4,
+                                                  c.stereo_calib_p2, c.image_shape, s.k_rpn_boxes, s.k_rpn_img_boxes)),
         "S3_rpn_crops": lambda s, p: ops.crop_and_resize_multi([(s.bev_1ch, s.k_bev_boxes, s.rpn_bev_crops),
                                                                 (s.img_1ch, s.k_img_boxes, s.rpn_img_crops)],
                                                                c.rpn_crop, 0.0, n_dev=s.n_kept),

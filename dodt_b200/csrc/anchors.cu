@@ -134,6 +134,56 @@ offset_to_anchor_kernel(const TA *__restrict__ anchors, const TO *__restrict__ o
   }
 }
 
+// What the reference does between the RPN head and NMS / the second-stage crops
+// (avod/core/models/dt_rpn_model.py:573-591,618-660): regressed anchors of the kept anchors,
+// projected into the BEV map and the image. One thread per kept anchor, float64 throughout.
+__global__ void __launch_bounds__(128)
+rpn_decode_kernel(const double *__restrict__ anchors, const float *__restrict__ offsets,
+                  const int *__restrict__ idx, const int *__restrict__ count, int n_max,
+                  double x_min, double x_max, double z_min, double z_max, const Calib P,
+                  double img_h, double img_w, float *__restrict__ bev_boxes,
+                  float *__restrict__ img_boxes) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= n_max || i >= __ldg(count)) return;
+  const size_t src = static_cast<size_t>(__ldg(idx + i));
+  const double *a = anchors + src * 6;
+  const float *o = offsets + src * 6;
+  double r[6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r[k] = __dadd_rn(__dmul_rn(static_cast<double>(__ldg(o + k)), __ldg(a + 3 + k)), __ldg(a + k));
+    r[3 + k] = exp(__dadd_rn(log(__ldg(a + 3 + k)), static_cast<double>(__ldg(o + 3 + k))));
+  }
+  const double hx = __ddiv_rn(r[3], 2.0), hz = __ddiv_rn(r[5], 2.0);
+  if (bev_boxes) {   // [z1, x1, z2, x2] normalised (project_to_bev + reorder_projected_boxes)
+    const double xr = __dsub_rn(x_max, x_min), zr = __dsub_rn(z_max, z_min);
+    const double x1 = __ddiv_rn(__dsub_rn(__dsub_rn(r[0], hx), x_min), xr);
+    const double x2 = __ddiv_rn(__dsub_rn(__dadd_rn(r[0], hx), x_min), xr);
+    const double z1 = __ddiv_rn(__dsub_rn(__dsub_rn(z_max, __dadd_rn(r[2], hz)), z_min), zr);
+    const double z2 = __ddiv_rn(__dsub_rn(__dsub_rn(z_max, __dsub_rn(r[2], hz)), z_min), zr);
+    reinterpret_cast<float4 *>(bev_boxes)[i] = make_float4(__double2float_rn(z1), __double2float_rn(x1),
+                                                           __double2float_rn(z2), __double2float_rn(x2));
+  }
+  if (img_boxes) {   // [y1, x1, y2, x2] normalised (project_to_image_space + reorder)
+    const double xs[2] = {__dadd_rn(r[0], hx), __dsub_rn(r[0], hx)};
+    const double ys[2] = {r[1], __dsub_rn(r[1], r[4])};
+    const double zs[2] = {__dadd_rn(r[2], hz), __dsub_rn(r[2], hz)};
+    double u_min = 0, u_max = 0, v_min = 0, v_max = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double cx = xs[k & 1], cy = ys[(k >> 1) & 1], cz = zs[(k >> 2) & 1];
+      const double w = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.p[8], cx), __dmul_rn(P.p[9], cy)), __dmul_rn(P.p[10], cz)), P.p[11]);
+      const double u = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.p[0], cx), __dmul_rn(P.p[1], cy)), __dmul_rn(P.p[2], cz)), P.p[3]), w);
+      const double v = __ddiv_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.p[4], cx), __dmul_rn(P.p[5], cy)), __dmul_rn(P.p[6], cz)), P.p[7]), w);
+      if (k == 0) { u_min = u_max = u; v_min = v_max = v; }
+      else { u_min = fmin(u_min, u); u_max = fmax(u_max, u); v_min = fmin(v_min, v); v_max = fmax(v_max, v); }
+    }
+    reinterpret_cast<float4 *>(img_boxes)[i] =
+        make_float4(__double2float_rn(__ddiv_rn(v_min, img_h)), __double2float_rn(__ddiv_rn(u_min, img_w)),
+                    __double2float_rn(__ddiv_rn(v_max, img_h)), __double2float_rn(__ddiv_rn(u_max, img_w)));
+  }
+}
+
 // np.arange(start, stop, step): length ceil((stop - start) / step), element i = start + i * delta
 // with delta = (start + step) - start
 int arange_len(double start, double stop, double step) {
@@ -261,6 +311,26 @@ int dodt_offset_to_anchor(const void *anchors, int32_t anchors_dtype, const void
     offset_to_anchor_kernel<float, double><<<blocks, 256, 0, stream>>>(static_cast<const float *>(anchors), static_cast<const double *>(offsets), n, out);
   else
     offset_to_anchor_kernel<float, float><<<blocks, 256, 0, stream>>>(static_cast<const float *>(anchors), static_cast<const float *>(offsets), n, out);
+  DODT_AFTER_LAUNCH();
+  return DODT_OK;
+}
+
+int dodt_rpn_decode(const double *anchors, const float *offsets, const int32_t *idx,
+                    const int32_t *count, int64_t n_max, const double bev_extents[4],
+                    const double p2[12], int32_t image_h, int32_t image_w, float *bev_boxes,
+                    float *img_boxes, dodt_stream_t stream_) {
+  using namespace dodt;
+  if (n_max < 0 || n_max > 0x7FFFFFFF || !count || !bev_extents) return DODT_EINVAL;
+  if (img_boxes && (!p2 || image_h <= 0 || image_w <= 0)) return DODT_EINVAL;
+  if (n_max == 0) return DODT_OK;
+  if (!anchors || !offsets || !idx || (!bev_boxes && !img_boxes)) return DODT_EINVAL;
+  if (reinterpret_cast<uintptr_t>(bev_boxes) % 16 != 0 || reinterpret_cast<uintptr_t>(img_boxes) % 16 != 0)
+    return DODT_EALIGN;
+  Calib P;
+  for (int k = 0; k < 12; ++k) P.p[k] = p2 ? p2[k] : 0.0;
+  rpn_decode_kernel<<<ceil_div(n_max, 128), 128, 0, as_stream(stream_)>>>(
+      anchors, offsets, idx, count, static_cast<int>(n_max), bev_extents[0], bev_extents[1],
+      bev_extents[2], bev_extents[3], P, image_h, image_w, bev_boxes, img_boxes);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }

@@ -33,11 +33,14 @@ class FrontEndConfig:
     height_lo: float = synth.HEIGHT_LO
     height_hi: float = synth.HEIGHT_HI
     num_slices: int = synth.NUM_SLICES
+    anchor_3d_sizes: list = field(default_factory=lambda: [list(v) for v in A.CAR_ANCHOR_SIZES])
+    anchor_stride: list = field(default_factory=lambda: list(synth.ANCHOR_STRIDE))
     occ_lo: float = 0.2
     occ_hi: float = 2.0
     density_threshold: int = 1
     max_points: int = 131072
     image_shape: tuple = synth.IMAGE_SHAPE          # (360, 1200)
+    stereo_calib_p2: list = field(default_factory=lambda: [float(v) for v in A.KITTI_P2.reshape(-1)])
     feat_channels: int = 32
     rpn_crop: tuple = (3, 3)                        # rpn_proposal_roi_crop_size
     rpn_nms_size: int = 1024                        # rpn_train_nms_size
@@ -90,8 +93,7 @@ class FrameSlot:
         self.sensor_buf = torch.empty(fe.sensor_bytes, dtype=torch.uint8, device=dev)
         v = _views(self.sensor_buf, fe.sensor_layout)
         self.points = v["points"]              # (3, max_points)
-        self.rpn_boxes = v["rpn_boxes"]        # regressed BEV boxes [z1,x1,z2,x2] normalised, per anchor
-        self.rpn_img_boxes = v["rpn_img_boxes"]  # regressed image boxes [y1,x1,y2,x2] normalised
+        self.rpn_offsets = v["rpn_offsets"]    # RPN regression output, anchor-form offsets per anchor
         self.rpn_scores = v["rpn_scores"]
         self.final_scores = v["final_scores"]
         self.frame_id = v["frame_id"]          # (sequence, frame) of the frame in this slot
@@ -134,8 +136,8 @@ class FrameSlot:
 
     def input_tensors(self):
         return dict(points=self.points, bev_feat=self.bev_feat, img_feat=self.img_feat,
-                    bev_1ch=self.bev_1ch, img_1ch=self.img_1ch, rpn_boxes=self.rpn_boxes,
-                    rpn_img_boxes=self.rpn_img_boxes, rpn_scores=self.rpn_scores,
+                    bev_1ch=self.bev_1ch, img_1ch=self.img_1ch, rpn_offsets=self.rpn_offsets,
+                    rpn_scores=self.rpn_scores,
                     final_scores=self.final_scores)
 
     def result_tensors(self):
@@ -174,8 +176,8 @@ class HostFrame:
                 self.sensor["points"][:, :self.n_points].copy_(t)
             elif k in self.features:
                 self.features[k].copy_(t)
-            else:
-                self.sensor[k].copy_(t)
+            elif k in self.sensor:
+                self.sensor[k].copy_(t)       # other keys (host-decoded boxes for the oracle) are not inputs
         return self
 
     @property
@@ -202,16 +204,21 @@ class FrontEnd:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
         self.nx, _, self.nz, self.min_x, _, self.min_z = ops.bev_grid(c.area_extents, c.voxel_size)
-        anchors = synth.car_anchors(c.area_extents, c.ground_plane) if anchors is None else anchors
-        self.anchors_np = np.ascontiguousarray(anchors, dtype=np.float64)
-        self.num_anchors = len(self.anchors_np)
-        bev_extents = [c.area_extents[0], c.area_extents[2]]
-        _, bev_norm = A.project_to_bev(self.anchors_np, bev_extents)
-        _, img_norm = A.project_to_image_space(self.anchors_np, A.KITTI_P2, c.image_shape)
-        to_dev = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(self.device)
-        self.anchors = to_dev(self.anchors_np, torch.float64)
-        self.anchor_bev_boxes = to_dev(A.reorder_projected_boxes(bev_norm), torch.float32)
-        self.anchor_img_boxes = to_dev(A.reorder_projected_boxes(img_norm), torch.float32)
+        with torch.cuda.device(self.device):
+            if anchors is None:
+                # the anchor grid of the config, generated on the device (bit-identical to
+                # box_3d_to_anchor(tile_anchors_3d(...)))
+                self.anchors = ops.grid_anchors(c.area_extents, c.anchor_3d_sizes, c.anchor_stride,
+                                                c.ground_plane, self.device)
+            else:
+                self.anchors = torch.from_numpy(np.ascontiguousarray(anchors, dtype=np.float64)).to(self.device)
+            self.num_anchors = int(self.anchors.shape[0])
+            self.bev_extents4 = [c.area_extents[0][0], c.area_extents[0][1],
+                                 c.area_extents[2][0], c.area_extents[2][1]]
+            # the anchors' own projections (crop boxes of the RPN stage, dt_rpn_model.py:975-985)
+            self.anchor_bev_boxes = ops.project_to_bev(self.anchors, self.bev_extents4, tf_order=True)
+            self.anchor_img_boxes = ops.project_to_image_space(self.anchors, c.stereo_calib_p2,
+                                                               c.image_shape, tf_order=True)
         _, _, self.corr_channels = ops.correlation_out_shape(
             self.nz, self.nx, 1, c.corr_max_displacement, 1, c.corr_stride_2, c.corr_padding)
         self.bev_params = ops.make_bev_params(c.ground_plane, c.area_extents, c.voxel_size,
@@ -221,8 +228,8 @@ class FrontEnd:
         f32, i32 = torch.float32, torch.int32
         nA = self.num_anchors
         self.sensor_layout, self.sensor_bytes = _layout([
-            ("points", (3, c.max_points), f32), ("rpn_boxes", (nA, 4), f32),
-            ("rpn_img_boxes", (nA, 4), f32), ("rpn_scores", (nA,), f32),
+            ("points", (3, c.max_points), f32), ("rpn_offsets", (nA, 6), f32),
+            ("rpn_scores", (nA,), f32),
             ("final_scores", (c.rpn_nms_size,), f32), ("frame_id", (2,), i32)])
         self.result_layout, self.result_bytes = _layout([
             ("n_kept", (1,), i32), ("n_top", (2,), i32), ("n_final", (2,), i32),
@@ -258,9 +265,11 @@ class FrontEnd:
             ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact)
             ops.gather_rows_multi([(self.anchor_bev_boxes, s.k_bev_boxes),
                                    (self.anchor_img_boxes, s.k_img_boxes),
-                                   (s.rpn_boxes, s.k_rpn_boxes),
-                                   (s.rpn_img_boxes, s.k_rpn_img_boxes),
                                    (s.rpn_scores, s.k_rpn_scores)], s.kept_idx, s.n_kept)
+            # RPN decode of the kept anchors (dt_rpn_model.py:573-591,618-660): regressed anchors
+            # projected into the BEV map and the image
+            ops.rpn_decode(self.anchors, s.rpn_offsets, s.kept_idx, s.n_kept, self.bev_extents4,
+                           c.stereo_calib_p2, c.image_shape, s.k_rpn_boxes, s.k_rpn_img_boxes)
         if "S3a" not in skip:
             ops.crop_and_resize_multi([(s.bev_1ch, s.k_bev_boxes, s.rpn_bev_crops),
                                        (s.img_1ch, s.k_img_boxes, s.rpn_img_crops)],

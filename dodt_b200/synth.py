@@ -62,12 +62,18 @@ def feature_pair(config, frame, shape=(1, 700, 800, 32)):
     return f0, f1.astype(np.float32)
 
 
+def rpn_offsets(config, frame, n):
+    """The RPN head's regression output for n anchors: float32 [n, 6] anchor-form offsets."""
+    rng = np.random.default_rng(1000 * config + frame + 700000)
+    return rng.normal(0.0, 0.1, (n, 6)).astype(np.float32)
+
+
 def rpn_proposals(config, frame, anchors_kept):
     """Regressed anchors, their normalised BEV boxes [x1,z1,x2,z2] (what dt_rpn_model.py:573-591
     hands to NMS) and tie-free scores."""
     rng = np.random.default_rng(1000 * config + frame + 700000)
     n = len(anchors_kept)
-    offsets = rng.normal(0.0, 0.1, (n, 6))
+    offsets = rng.normal(0.0, 0.1, (n, 6)).astype(np.float32).astype(np.float64)   # == rpn_offsets
     regressed = A.offset_to_anchor(anchors_kept, offsets)
     _, bev_norm = A.project_to_bev(regressed, BEV_EXTENTS)
     scores = rng.permutation(np.linspace(0.01, 0.99, n)).astype(np.float32)
@@ -100,7 +106,9 @@ def anchor_set():
 
 def frame_inputs(config, frame, n_points=120000, rpn_nms_size=1024):
     """Host inputs of one frame slot (dodt_b200.frontend.FrameSlot): synthetic sensor data and
-    synthetic network-head outputs, a pure function of (config, frame)."""
+    synthetic network-head outputs, a pure function of (config, frame). `rpn_offsets` is what the
+    slot consumes; `rpn_boxes` / `rpn_img_boxes` are the same offsets decoded and projected on the
+    host (the reference's NumPy chain), for the CPU oracle."""
     a, _, _ = anchor_set()
     rng = np.random.default_rng(1000 * config + frame + 900000)
     bev_feat, _ = feature_pair(config, frame)                          # [1,700,800,32]
@@ -112,6 +120,7 @@ def frame_inputs(config, frame, n_points=120000, rpn_nms_size=1024):
         bev_feat=bev_feat, img_feat=img_feat,
         bev_1ch=np.ascontiguousarray(bev_feat[..., :1]) * np.float32(0.5),
         img_1ch=np.ascontiguousarray(img_feat[..., :1]) * np.float32(0.5),
+        rpn_offsets=rpn_offsets(config, frame, len(a)),
         rpn_boxes=A.reorder_projected_boxes(bev_norm).astype(np.float32),
         rpn_img_boxes=A.reorder_projected_boxes(img_norm).astype(np.float32),
         rpn_scores=scores,

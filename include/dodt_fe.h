@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DODT_FE_VERSION 104 /* major*100 + minor */
+#define DODT_FE_VERSION 105 /* major*100 + minor */
 
 typedef void *dodt_stream_t; /* cudaStream_t */
 
@@ -195,6 +195,16 @@ int dodt_project_to_image_space(const void *anchors, int32_t dtype, int64_t n, c
 /* avod/core/anchor_encoder.py:99-150 (offset_to_anchor): out float64 [n, 6]. */
 int dodt_offset_to_anchor(const void *anchors, int32_t anchors_dtype, const void *offsets,
                           int32_t offsets_dtype, int64_t n, double *out, dodt_stream_t stream);
+
+/* The decode chain between the RPN head and NMS / the second-stage crops
+ * (avod/core/models/dt_rpn_model.py:573-591,618-660) for the anchors a device-side filter kept:
+ * for i < *count: regressed = offset_to_anchor(anchors[idx[i]], offsets[idx[i]]);
+ * bev_boxes[i] = normalised BEV corners [z1, x1, z2, x2]; img_boxes[i] = normalised image corners
+ * [y1, x1, y2, x2] (either output may be NULL). anchors [m, 6] float64, offsets [m, 6] float32. */
+int dodt_rpn_decode(const double *anchors, const float *offsets, const int32_t *idx,
+                    const int32_t *count, int64_t n_max, const double bev_extents[4],
+                    const double p2[12], int32_t image_h, int32_t image_w, float *bev_boxes,
+                    float *img_boxes, dodt_stream_t stream);
 
 /* Multi-GPU hand-off (the per-frame rows the reference writes with np.savetxt,
  * avod/core/dt_evaluator.py:1098-1147, and that a sharded run gathers once per shard): appends the

@@ -18,6 +18,26 @@ def _upload(slot, inp):
             dst.copy_(src)
 
 
+def _reference_frame(fe, slot, inp, prev_bev_feat):
+    """The CPU oracle's frame, with the RPN-decode boxes taken from the device after checking that
+    they equal the host NumPy chain to float64 rounding noise (exp/log and np.dot are library
+    defined; everything downstream is then compared exactly / to 1e-5)."""
+    from oracle import cpu_frontend
+    n_kept = int(slot.n_kept.item())
+    kept = slot.kept_idx[:n_kept].cpu().numpy()
+    k_boxes = slot.k_rpn_boxes[:n_kept].cpu().numpy()
+    k_img = slot.k_rpn_img_boxes[:n_kept].cpu().numpy()
+    np.testing.assert_allclose(k_boxes, inp["rpn_boxes"][kept], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(k_img, inp["rpn_img_boxes"][kept], rtol=1e-6, atol=1e-7)
+    assert (k_boxes == inp["rpn_boxes"][kept]).mean() > 0.98
+    a_img = fe.anchor_img_boxes.cpu().numpy()
+    np.testing.assert_allclose(a_img, cpu_frontend.anchors()[2], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(fe.anchors.cpu().numpy(), cpu_frontend.anchors()[0])
+    np.testing.assert_array_equal(fe.anchor_bev_boxes.cpu().numpy(), cpu_frontend.anchors()[1])
+    return cpu_frontend.run_frame(inp, prev_bev_feat, k_boxes=k_boxes, k_img_boxes=k_img,
+                                  anchor_img_boxes=a_img)
+
+
 def _check(slot, ref):
     n_kept = int(slot.n_kept.item())
     assert n_kept == len(ref["kept"])
@@ -54,7 +74,7 @@ def test_frontend_frame_eager_and_graph(lib):
     launches = fe.enqueue(slots[1], slots[0])
     torch.cuda.synchronize()
     assert launches > 10
-    ref = cpu_frontend.run_frame(inputs[1], inputs[0]["bev_feat"])
+    ref = _reference_frame(fe, slots[1], inputs[1], inputs[0]["bev_feat"])
     _check(slots[1], ref)
     # the same frame as a CUDA-graph replay, after scribbling over the outputs
     graph, n = fe.capture(slots[1], slots[0])
@@ -68,7 +88,7 @@ def test_frontend_frame_eager_and_graph(lib):
     _upload(slots[1], synth.frame_inputs(2, 42))
     graph.replay()
     torch.cuda.synchronize()
-    ref2 = cpu_frontend.run_frame(synth.frame_inputs(2, 42), inputs[0]["bev_feat"])
+    ref2 = _reference_frame(fe, slots[1], synth.frame_inputs(2, 42), inputs[0]["bev_feat"])
     _check(slots[1], ref2)
 
 
@@ -132,13 +152,13 @@ def test_host_frame_and_detection_block(lib):
     graph.replay()
     hosts[1].download(slots[1])
     torch.cuda.synchronize()
-    ref = cpu_frontend.run_frame(inputs[1], inputs[0]["bev_feat"])
+    ref = _reference_frame(fe, slots[1], inputs[1], inputs[0]["bev_feat"])
     _check(slots[1], ref)
     got = shard.gather_detections(block)
     assert list(got) == [(3, 51)]
     rows = got[(3, 51)].numpy()
     kept = ref["kept"]
-    prop = inputs[1]["rpn_boxes"][kept][ref["top"]]
+    prop = slots[1].k_rpn_boxes[:len(kept)].cpu().numpy()[ref["top"]]
     np.testing.assert_array_equal(rows[:, 5].astype(np.int64), ref["final"])
     np.testing.assert_array_equal(rows[:, :4], prop[ref["final"]])
     np.testing.assert_array_equal(rows[:, 4], inputs[1]["final_scores"][ref["final"]])
