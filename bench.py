@@ -324,7 +324,7 @@ def run_ours(args):
                                                           (fe.anchor_img_boxes, s.k_img_boxes),
                                                           (s.rpn_scores, s.k_rpn_scores)], s.kept_idx, s.n_kept),
                                    ops.rpn_decode(fe.anchors, s.rpn_offsets, s.kept_idx, s.n_kept, fe.bev_extents4,
-                                                  c.stereo_calib_p2, c.image_shape, s.k_rpn_boxes, s.k_rpn_img_boxes)),
+                                                  c.stereo_calib_p2, c.image_shape, s.k_rpn_boxes, None)),
         "S3_rpn_crops": lambda s, p: ops.crop_and_resize_multi([(s.bev_1ch, s.k_bev_boxes, s.rpn_bev_crops),
                                                                 (s.img_1ch, s.k_img_boxes, s.rpn_img_crops)],
                                                                c.rpn_crop, 0.0, n_dev=s.n_kept),

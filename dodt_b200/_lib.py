@@ -82,7 +82,7 @@ SIGNATURES = {
     "dodt_project_to_image_space": (c_int, [c_void_p, c_int32, c_int64, POINTER(c_double), c_int32,
                                             c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dodt_offset_to_anchor": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
-    "dodt_rpn_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double),
+    "dodt_rpn_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double),
                                 POINTER(c_double), c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dodt_emit_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),

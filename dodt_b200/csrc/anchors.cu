@@ -139,13 +139,14 @@ offset_to_anchor_kernel(const TA *__restrict__ anchors, const TO *__restrict__ o
 // projected into the BEV map and the image. One thread per kept anchor, float64 throughout.
 __global__ void __launch_bounds__(128)
 rpn_decode_kernel(const double *__restrict__ anchors, const float *__restrict__ offsets,
-                  const int *__restrict__ idx, const int *__restrict__ count, int n_max,
+                  const int *__restrict__ idx, const int *__restrict__ idx2,
+                  const int *__restrict__ count, int n_max,
                   double x_min, double x_max, double z_min, double z_max, const Calib P,
                   double img_h, double img_w, float *__restrict__ bev_boxes,
                   float *__restrict__ img_boxes) {
   const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= n_max || i >= __ldg(count)) return;
-  const size_t src = static_cast<size_t>(__ldg(idx + i));
+  const size_t src = static_cast<size_t>(__ldg(idx + (idx2 ? __ldg(idx2 + i) : i)));
   const double *a = anchors + src * 6;
   const float *o = offsets + src * 6;
   double r[6];
@@ -316,7 +317,8 @@ int dodt_offset_to_anchor(const void *anchors, int32_t anchors_dtype, const void
 }
 
 int dodt_rpn_decode(const double *anchors, const float *offsets, const int32_t *idx,
-                    const int32_t *count, int64_t n_max, const double bev_extents[4],
+                    const int32_t *idx2, const int32_t *count, int64_t n_max,
+                    const double bev_extents[4],
                     const double p2[12], int32_t image_h, int32_t image_w, float *bev_boxes,
                     float *img_boxes, dodt_stream_t stream_) {
   using namespace dodt;
@@ -329,7 +331,7 @@ int dodt_rpn_decode(const double *anchors, const float *offsets, const int32_t *
   Calib P;
   for (int k = 0; k < 12; ++k) P.p[k] = p2 ? p2[k] : 0.0;
   rpn_decode_kernel<<<ceil_div(n_max, 128), 128, 0, as_stream(stream_)>>>(
-      anchors, offsets, idx, count, static_cast<int>(n_max), bev_extents[0], bev_extents[1],
+      anchors, offsets, idx, idx2, count, static_cast<int>(n_max), bev_extents[0], bev_extents[1],
       bev_extents[2], bev_extents[3], P, image_h, image_w, bev_boxes, img_boxes);
   DODT_AFTER_LAUNCH();
   return DODT_OK;

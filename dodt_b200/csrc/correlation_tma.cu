@@ -260,7 +260,9 @@ struct CorrAsyncGeom {
 
 // PX pixels per thread (spaced 2 apart). PX = 4: 256 threads, 100 accumulators, 10 FMAs per
 // shared-memory float; PX = 2: 512 threads (16 warps), 50 accumulators, 6.7 FMAs per float.
-template <int R, int PX, int FRONT, int TH, int CTAS>
+// NST: stages of the cp.async ring (unit u lives in stage u % NST and is requested NST-1 units
+// ahead of its use).
+template <int R, int PX, int FRONT, int TH, int CTAS, int NST>
 __global__ void __launch_bounds__(kTW / (2 * PX) * 2 * TH, CTAS)
 corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const CorrAsyncGeom g,
               float *__restrict__ out) {
@@ -304,7 +306,7 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     const int tx = tile % g.tiles_x;
     const int ty = (tile / g.tiles_x) % g.tiles_y;
     const int n = tile / (g.tiles_x * g.tiles_y);
-    const uint32_t sbase = smem_base + ((u & 1) ? Cfg::STAGE1_OFF : 0);
+    const uint32_t sbase = smem_base + static_cast<uint32_t>(u % NST) * Cfg::STAGE1_OFF;
     const size_t img = static_cast<size_t>(n) * g.H * g.W * g.C;
 #pragma unroll
     for (int rr = 0; rr < kRowsPerThread; ++rr) {
@@ -355,7 +357,11 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
 #pragma unroll
   for (int q = 0; q < NB; ++q) boff[q] = swz(row * Cfg::BW + x0 + 2 * q, 0);
 
-  if (n_units > 0) issue(0);
+#pragma unroll
+  for (int u0 = 0; u0 < NST - 1; ++u0) {
+    if (u0 < n_units) issue(u0);
+    else asm volatile("cp.async.commit_group;" ::: "memory");   // keep the group count uniform
+  }
   int it = 0;
   for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
     float acc[PX][D2];
@@ -366,12 +372,12 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
 
     int stage = 0;
     for (int ch = 0; ch < n_chunks; ++ch, ++it) {
-      stage = it & 1;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      stage = it % NST;
+      asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");
       __syncthreads();   // unit `it` has landed for everyone; everyone is done with unit it-1
-      const bool more = it + 1 < n_units;
-      if (more) prepare(it + 1);
-      const float *sa = reinterpret_cast<const float *>(smem + (stage ? Cfg::STAGE1_OFF : 0));
+      const bool more = it + NST - 1 < n_units;
+      if (more) prepare(it + NST - 1);
+      const float *sa = reinterpret_cast<const float *>(smem + stage * Cfg::STAGE1_OFF);
       const float *sb = sa + Cfg::A_BYTES / 4;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -418,7 +424,8 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     const int ty = (tile / g.tiles_x) % g.tiles_y;
     const int n = tile / (g.tiles_x * g.tiles_y);
     float *stg = reinterpret_cast<float *>(
-        smem + (stage ? Cfg::STAGE1_OFF + Cfg::STAGE_BYTES - Cfg::OUT_BYTES : 0));
+        smem + (stage == NST - 1 ? stage * Cfg::STAGE1_OFF + Cfg::STAGE_BYTES - Cfg::OUT_BYTES
+                                 : stage * Cfg::STAGE1_OFF));
     __syncthreads();  // everyone is done reading this stage
     if (g.pow2) {
 #pragma unroll
@@ -517,15 +524,17 @@ int launch(const float *a, const float *b, int N, int H, int W, int C, int out_h
   return DODT_OK;
 }
 
-template <int R, int PX, int FRONT, int TH = kTH, int CTAS = 1>
+template <int R, int PX, int FRONT, int TH = kTH, int CTAS = 1, int NST = 2>
 int launch_async(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w,
                  int shift, float *out, int max_ctas, cudaStream_t stream) {
   using Cfg = TmaCfg<R, TH>;
   constexpr int kThr = kTW / (2 * PX) * 2 * TH;
+  constexpr int smem_bytes = (NST - 1) * Cfg::STAGE1_OFF + Cfg::STAGE_BYTES + 64;
+  static_assert(NST == 2 || Cfg::SPARE == 0, "the staging spare region is laid out for two stages");
   static bool attr_set = false;
   if (!attr_set) {
-    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R, PX, FRONT, TH, CTAS>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R, PX, FRONT, TH, CTAS, NST>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   CorrAsyncGeom g;
@@ -537,7 +546,7 @@ int launch_async(const float *a, const float *b, int N, int H, int W, int C, int
   g.inv_c = 1.0f / static_cast<float>(C);
   int grid = g.n_tiles < CTAS * kNumSMs ? g.n_tiles : CTAS * kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;   // persistent CTAs: any count works
-  corr_async_k1<R, PX, FRONT, TH, CTAS><<<grid, kThr, Cfg::SMEM_BYTES, stream>>>(a, b, g, out);
+  corr_async_k1<R, PX, FRONT, TH, CTAS, NST><<<grid, kThr, smem_bytes, stream>>>(a, b, g, out);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }
@@ -554,7 +563,7 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
   static int impl = -1;
   if (impl < 0) {
     const char *e = getenv("DODT_CORR_IMPL");
-    impl = (e && e[0] == 't') ? 1 : ((e && e[0] == '2') ? 2 : ((e && e[0] == 'f') ? 3 : ((e && e[0] == '1') ? 4 : 0)));
+    impl = (e && e[0] == 't') ? 1 : ((e && e[0] == '2') ? 2 : ((e && e[0] == 'f') ? 3 : ((e && e[0] == '1') ? 4 : ((e && e[0] == '3') ? 6 : 0))));
   }
   if (impl == 1) {
     switch (r) {
@@ -574,6 +583,13 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
     switch (r) {
       case 1: return launch_async<1, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
       case 2: return launch_async<2, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+      default: return 1;
+    }
+  }
+  if (impl == 6) {   // three-stage ring, 8-row tiles, one CTA per SM
+    switch (r) {
+      case 1: return launch_async<1, 4, 0, 8, 1, 3>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+      case 2: return launch_async<2, 4, 0, 8, 1, 3>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
       default: return 1;
     }
   }

@@ -116,7 +116,6 @@ class FrameSlot:
         self.k_bev_boxes = e(nA, 4)
         self.k_img_boxes = e(nA, 4)
         self.k_rpn_boxes = e(nA, 4)
-        self.k_rpn_img_boxes = e(nA, 4)
         self.k_rpn_scores = e(nA)
         self.rpn_bev_crops = e(nA, c.rpn_crop[0], c.rpn_crop[1], 1)
         self.rpn_img_crops = e(nA, c.rpn_crop[0], c.rpn_crop[1], 1)
@@ -269,7 +268,7 @@ class FrontEnd:
             # RPN decode of the kept anchors (dt_rpn_model.py:573-591,618-660): regressed anchors
             # projected into the BEV map and the image
             ops.rpn_decode(self.anchors, s.rpn_offsets, s.kept_idx, s.n_kept, self.bev_extents4,
-                           c.stereo_calib_p2, c.image_shape, s.k_rpn_boxes, s.k_rpn_img_boxes)
+                           c.stereo_calib_p2, c.image_shape, s.k_rpn_boxes, None)
         if "S3a" not in skip:
             ops.crop_and_resize_multi([(s.bev_1ch, s.k_bev_boxes, s.rpn_bev_crops),
                                        (s.img_1ch, s.k_img_boxes, s.rpn_img_crops)],
@@ -278,8 +277,10 @@ class FrontEnd:
             ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx,
                     n_keep=s.n_top, workspace=s.ws_nms_rpn, n_dev=s.n_kept,
                     max_windows=c.nms_max_windows)
-            ops.gather_rows_multi([(s.k_rpn_boxes, s.prop_bev_boxes),
-                                   (s.k_rpn_img_boxes, s.prop_img_boxes)], s.top_idx, s.n_top)
+            ops.gather_rows_multi([(s.k_rpn_boxes, s.prop_bev_boxes)], s.top_idx, s.n_top)
+            # image boxes only for the proposals that survived (eight fp64 corner projections each)
+            ops.rpn_decode(self.anchors, s.rpn_offsets, s.kept_idx, s.n_top, self.bev_extents4,
+                           c.stereo_calib_p2, c.image_shape, None, s.prop_img_boxes, idx2=s.top_idx)
         # S3b (the corr crop needs S4)
         main.wait_stream(self.side_stream)
         if "S3b" not in skip:

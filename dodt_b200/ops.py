@@ -285,15 +285,17 @@ def offset_to_anchor(anchors, offsets):
 
 
 def rpn_decode(anchors, offsets, idx, count, bev_extents, stereo_calib_p2, image_shape, bev_boxes,
-               img_boxes):
-    """Regressed + projected boxes of the anchors idx[:count[0]] (device-side count):
-    bev_boxes [n_max, 4] [z1,x1,z2,x2], img_boxes [n_max, 4] [y1,x1,y2,x2], float32, normalised."""
-    _need_cuda(anchors, offsets, idx, count, bev_boxes, img_boxes)
+               img_boxes, idx2=None):
+    """Regressed + projected boxes of the anchors idx[:count[0]] (device-side count), or of
+    idx[idx2[:count[0]]]: bev_boxes [n_max, 4] [z1,x1,z2,x2], img_boxes [n_max, 4] [y1,x1,y2,x2],
+    float32, normalised; either may be None."""
+    _need_cuda(anchors, offsets, idx, count, bev_boxes, img_boxes, idx2)
     if anchors.dtype != torch.float64 or offsets.dtype != torch.float32:
         raise TypeError("rpn_decode expects float64 anchors and float32 offsets")
     if not (anchors.is_contiguous() and offsets.is_contiguous()):
         raise ValueError("rpn_decode needs contiguous tensors")
-    check(load().dodt_rpn_decode(_ptr(anchors), _ptr(offsets), _ptr(idx), _ptr(count), idx.numel(),
+    n_max = (bev_boxes if bev_boxes is not None else img_boxes).shape[0]
+    check(load().dodt_rpn_decode(_ptr(anchors), _ptr(offsets), _ptr(idx), _ptr(idx2), _ptr(count), n_max,
                                  _dbl(bev_extents, 4), _dbl(stereo_calib_p2, 12), int(image_shape[0]),
                                  int(image_shape[1]), _ptr(bev_boxes), _ptr(img_boxes), _stream()),
           "dodt_rpn_decode")

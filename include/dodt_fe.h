@@ -198,11 +198,14 @@ int dodt_offset_to_anchor(const void *anchors, int32_t anchors_dtype, const void
 
 /* The decode chain between the RPN head and NMS / the second-stage crops
  * (avod/core/models/dt_rpn_model.py:573-591,618-660) for the anchors a device-side filter kept:
- * for i < *count: regressed = offset_to_anchor(anchors[idx[i]], offsets[idx[i]]);
+ * for i < *count: j = idx[idx2 ? idx2[i] : i]; regressed = offset_to_anchor(anchors[j], offsets[j]);
  * bev_boxes[i] = normalised BEV corners [z1, x1, z2, x2]; img_boxes[i] = normalised image corners
- * [y1, x1, y2, x2] (either output may be NULL). anchors [m, 6] float64, offsets [m, 6] float32. */
+ * [y1, x1, y2, x2] (either output may be NULL). anchors [m, 6] float64, offsets [m, 6] float32.
+ * idx2 (optional) selects among the kept anchors, e.g. the NMS survivors: the image projection
+ * (eight corners in float64) is only needed for those. n_max bounds i. */
 int dodt_rpn_decode(const double *anchors, const float *offsets, const int32_t *idx,
-                    const int32_t *count, int64_t n_max, const double bev_extents[4],
+                    const int32_t *idx2, const int32_t *count, int64_t n_max,
+                    const double bev_extents[4],
                     const double p2[12], int32_t image_h, int32_t image_w, float *bev_boxes,
                     float *img_boxes, dodt_stream_t stream);
 

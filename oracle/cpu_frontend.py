@@ -21,11 +21,12 @@ frame_inputs = s.frame_inputs
 
 
 def run_frame(inp, prev_bev_feat, rpn_nms=(1024, 0.8), avod_nms=(100, 0.01), timings=None,
-              k_boxes=None, k_img_boxes=None, anchor_img_boxes=None):
+              k_boxes=None, prop_img_boxes=None, anchor_img_boxes=None):
     """All stages of one frame; returns the outputs FrontEnd produces (for parity).
 
     The RPN decode (offset_to_anchor + projections) is the reference's NumPy chain, precomputed in
-    inp["rpn_boxes"] / inp["rpn_img_boxes"]; k_boxes / k_img_boxes (boxes of the KEPT anchors) and
+    inp["rpn_boxes"] / inp["rpn_img_boxes"]; k_boxes (BEV boxes of the KEPT anchors),
+    prop_img_boxes (image boxes of the NMS survivors, or a callable top -> boxes) and
     anchor_img_boxes replace them when a test wants the later stages judged on exactly the boxes
     the device produced (those agree with NumPy to float64 rounding noise, see tests)."""
     a, a_bev, a_img = anchors()
@@ -55,8 +56,7 @@ def run_frame(inp, prev_bev_feat, rpn_nms=(1024, 0.8), avod_nms=(100, 0.01), tim
     k_scores = inp["rpn_scores"][kept]
     if k_boxes is None:
         k_boxes = inp["rpn_boxes"][kept]
-    if k_img_boxes is None:
-        k_img_boxes = inp["rpn_img_boxes"][kept]
+
     top = CO.non_max_suppression(k_boxes, k_scores, rpn_nms[0], rpn_nms[1])
     t["S5_rpn"] = tic() - t0
     t0 = tic()
@@ -64,7 +64,10 @@ def run_frame(inp, prev_bev_feat, rpn_nms=(1024, 0.8), avod_nms=(100, 0.01), tim
     t["S4"] = tic() - t0
     t0 = tic()
     prop_bev = k_boxes[top]
-    prop_img = k_img_boxes[top]
+    if prop_img_boxes is None:
+        prop_img = inp["rpn_img_boxes"][kept][top]
+    else:
+        prop_img = prop_img_boxes(top) if callable(prop_img_boxes) else prop_img_boxes
     z = np.zeros(len(top), dtype=np.int32)
     bev_rois = CO.crop_and_resize(inp["bev_feat"], prop_bev, z, (7, 7))
     img_rois = CO.crop_and_resize(inp["img_feat"], prop_img, z, (7, 7))

@@ -26,15 +26,18 @@ def _reference_frame(fe, slot, inp, prev_bev_feat):
     n_kept = int(slot.n_kept.item())
     kept = slot.kept_idx[:n_kept].cpu().numpy()
     k_boxes = slot.k_rpn_boxes[:n_kept].cpu().numpy()
-    k_img = slot.k_rpn_img_boxes[:n_kept].cpu().numpy()
     np.testing.assert_allclose(k_boxes, inp["rpn_boxes"][kept], rtol=1e-6, atol=1e-7)
-    np.testing.assert_allclose(k_img, inp["rpn_img_boxes"][kept], rtol=1e-6, atol=1e-7)
     assert (k_boxes == inp["rpn_boxes"][kept]).mean() > 0.98
+
+    def prop_img(top):   # image boxes exist on the device for the NMS survivors only
+        got = slot.prop_img_boxes[:len(top)].cpu().numpy()
+        np.testing.assert_allclose(got, inp["rpn_img_boxes"][kept][top], rtol=1e-6, atol=1e-7)
+        return got
     a_img = fe.anchor_img_boxes.cpu().numpy()
     np.testing.assert_allclose(a_img, cpu_frontend.anchors()[2], rtol=1e-6, atol=1e-7)
     np.testing.assert_array_equal(fe.anchors.cpu().numpy(), cpu_frontend.anchors()[0])
     np.testing.assert_array_equal(fe.anchor_bev_boxes.cpu().numpy(), cpu_frontend.anchors()[1])
-    return cpu_frontend.run_frame(inp, prev_bev_feat, k_boxes=k_boxes, k_img_boxes=k_img,
+    return cpu_frontend.run_frame(inp, prev_bev_feat, k_boxes=k_boxes, prop_img_boxes=prop_img,
                                   anchor_img_boxes=a_img)
 
 

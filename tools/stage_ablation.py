@@ -43,7 +43,9 @@ def run(skip):
 
 
 base = run(())
-print("all stages: %.1f us/frame (%.0f frames/s)" % (base, 1e6 / base))
+print("all stages: %.1f us/frame (%.0f frames/s)" % (base, 1e6 / base), flush=True)
+if len(sys.argv) > 3 and sys.argv[3] == "base":
+    sys.exit(0)
 for st in ("S1", "S2", "S3a", "S5a", "S4", "S3b", "S5b"):
     t = run((st,))
     print("without %-3s: %6.1f us/frame  (stage costs %5.1f us of throughput)" % (st, t, base - t))
