@@ -17,7 +17,7 @@ OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(HERE, "libdodt_fe.so")
 
 SOURCES = ["common.cu", "bev_slices.cu", "anchor_filter.cu", "crop_resize.cu", "correlation.cu", "correlation_tma.cu",
-           "nms.cu", "frontend.cu", "anchors.cu"]
+           "nms.cu", "frontend.cu", "anchors.cu", "lidar.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

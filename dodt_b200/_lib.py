@@ -56,7 +56,11 @@ SIGNATURES = {
     "dodt_launch_count": (c_int64, []),
     "dodt_bev_grid": (c_int, [POINTER(c_double), c_double, POINTER(c_int32)]),
     "dodt_bev_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
-    "dodt_bev_slices": (c_int, [c_void_p, c_int32, c_int64, c_int64, POINTER(BevParams), c_void_p,
+    "dodt_lidar_workspace_bytes": (c_size_t, [c_int64]),
+    "dodt_lidar_to_camera": (c_int, [c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int32,
+                                     c_int32, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
+    "dodt_bev_slices": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int64, POINTER(BevParams), c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                 c_void_p]),
     "dodt_integral_workspace_bytes": (c_size_t, [c_int32, c_int32]),

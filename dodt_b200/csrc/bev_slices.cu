@@ -119,7 +119,8 @@ struct BlockStage {
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kBlock)
 bev_accumulate(const T *__restrict__ px, const T *__restrict__ py, const T *__restrict__ pz,
-               long long n, int vec_ok, const __grid_constant__ BevDev P,
+               long long n_max, const int *__restrict__ n_dev, int vec_ok,
+               const __grid_constant__ BevDev P,
                unsigned *__restrict__ maps, unsigned char *__restrict__ occ,
                int *__restrict__ stats) {
   __shared__ BlockStage st;
@@ -128,6 +129,7 @@ bev_accumulate(const T *__restrict__ px, const T *__restrict__ py, const T *__re
   if (threadIdx.x < DODT_MAX_SLICES + 2) st.slice_pts[threadIdx.x] = 0;
   __syncthreads();
 
+  const long long n = n_dev ? min(n_max, static_cast<long long>(__ldg(n_dev))) : n_max;
   const long long i0 = (static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x) * VEC;
   T x[VEC], y[VEC], z[VEC];
   if (vec_ok && i0 + VEC <= n) {
@@ -351,7 +353,8 @@ size_t dodt_bev_workspace_bytes(int64_t n_points, int32_t num_slices, int32_t nx
   return 256;   // no scratch is needed any more (keys and counts live in the maps); kept in the ABI
 }
 
-int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, int64_t row_stride,
+int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, const int32_t *n_dev,
+                    int64_t row_stride,
                     const dodt_bev_params *p, float *maps, uint8_t *occ, int32_t *stats,
                     int32_t *winner_idx, int32_t *counts, void *workspace,
                     size_t workspace_bytes, dodt_stream_t stream_) {
@@ -457,9 +460,9 @@ int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, int64_t row_s
       const int vec_ok = (reinterpret_cast<uintptr_t>(px) % 16 == 0 && row_stride % 4 == 0) ? 1 : 0;
       const int blocks = ceil_div(n, static_cast<int64_t>(kBlock) * vec);
       if (dense)
-        bev_accumulate<float, 4><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, vec_ok, P, umaps, occ, stats);
+        bev_accumulate<float, 4><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, n_dev, vec_ok, P, umaps, occ, stats);
       else
-        bev_accumulate<float, 1><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, 1, P, umaps, occ, stats);
+        bev_accumulate<float, 1><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, n_dev, 1, P, umaps, occ, stats);
       DODT_AFTER_LAUNCH();
     }
     if (HW % 4 == 0)
@@ -476,9 +479,9 @@ int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, int64_t row_s
       const int vec_ok = (reinterpret_cast<uintptr_t>(px) % 16 == 0 && row_stride % 2 == 0) ? 1 : 0;
       const int blocks = ceil_div(n, static_cast<int64_t>(kBlock) * vec);
       if (dense)
-        bev_accumulate<double, 2><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, vec_ok, P, umaps, occ, stats);
+        bev_accumulate<double, 2><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, n_dev, vec_ok, P, umaps, occ, stats);
       else
-        bev_accumulate<double, 1><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, 1, P, umaps, occ, stats);
+        bev_accumulate<double, 1><<<blocks, kBlock, 0, stream>>>(px, py, pz, n, n_dev, 1, P, umaps, occ, stats);
       DODT_AFTER_LAUNCH();
     }
     if (HW % 4 == 0)

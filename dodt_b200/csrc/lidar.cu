@@ -1,0 +1,122 @@
+// LiDAR ingest: raw velodyne scan -> camera-frame points inside the image
+// frustum, the step in front of S1. Host NumPy in the reference:
+//   wavedata/wavedata/tools/core/calib_utils.py:484-523          lidar_to_cam_frame
+//   wavedata/wavedata/tools/core/calib_utils.py:394-410          project_to_image
+//   wavedata/wavedata/tools/obj_detection/tracking_utils.py:152-203  get_lidar_point_cloud
+//       (points with camera z > 0 whose projection lies strictly inside the image, input order)
+//
+// One pass computes the rectified camera coordinates (float64, as the reference: np.dot of float64
+// calibration matrices) and the keep flag of every point; the ordered compaction reuses the
+// front end's compact kernels; a gather writes the (3, M) structure-of-arrays cloud S1 consumes.
+// np.dot's summation order / FMA use is BLAS-defined, so coordinates agree with NumPy to float64
+// rounding noise (the keep decision could differ only for a point whose projection is within that
+// noise of the image border).
+#include "common.cuh"
+
+namespace dodt {
+namespace {
+
+struct LidarGeom {
+  double m[12];   // rows 0..2 of R0_rect(4x4) . Tr_velo_to_cam(4x4)
+  double p[12];   // camera matrix P2
+  double im_w, im_h;
+  int filter;     // 0: keep every point (im_size not given)
+};
+
+__global__ void __launch_bounds__(256)
+lidar_transform(const float4 *__restrict__ velo, long long n, const LidarGeom g,
+                double *__restrict__ cam /* (3, n) */, unsigned char *__restrict__ keep) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = __ldg(velo + i);
+  const double x = v.x, y = v.y, z = v.z;
+  double c[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    c[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.m[4 * r], x), __dmul_rn(g.m[4 * r + 1], y)),
+                               __dmul_rn(g.m[4 * r + 2], z)), g.m[4 * r + 3]);
+  cam[i] = c[0];
+  cam[n + i] = c[1];
+  cam[2 * n + i] = c[2];
+  bool k = true;
+  if (g.filter) {
+    k = c[2] > 0.0;   // in front of the camera
+    double q[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      q[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.p[4 * r], c[0]), __dmul_rn(g.p[4 * r + 1], c[1])),
+                                 __dmul_rn(g.p[4 * r + 2], c[2])), g.p[4 * r + 3]);
+    const double u = __ddiv_rn(q[0], q[2]), w = __ddiv_rn(q[1], q[2]);
+    k = k && u > 0.0 && u < g.im_w && w > 0.0 && w < g.im_h;
+  }
+  keep[i] = k ? 1 : 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+lidar_gather(const double *__restrict__ cam, long long n, const int *__restrict__ idx,
+             const int *__restrict__ count, long long out_stride, T *__restrict__ out) {
+  const long long j = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (j >= n || j >= __ldg(count)) return;
+  const long long src = __ldg(idx + j);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) out[r * out_stride + j] = static_cast<T>(cam[r * n + src]);
+}
+
+}  // namespace
+}  // namespace dodt
+
+extern "C" {
+
+size_t dodt_lidar_workspace_bytes(int64_t n) {
+  if (n < 0) return 0;
+  const size_t nn = static_cast<size_t>(n > 0 ? n : 1);
+  // camera coordinates (3n doubles), keep flags, kept indices, the compaction's own scratch
+  return 3 * nn * sizeof(double) + ((nn + 255) & ~static_cast<size_t>(255)) + nn * sizeof(int32_t) + 256 +
+         dodt_compact_workspace_bytes(n) + 256;
+}
+
+int dodt_lidar_to_camera(const float *velo, int64_t n, const double rectified[12],
+                         const double p2[12], int32_t image_w, int32_t image_h, void *points,
+                         int32_t points_dtype, int64_t row_stride, int32_t *count, void *workspace,
+                         size_t workspace_bytes, dodt_stream_t stream_) {
+  using namespace dodt;
+  if (n < 0 || n > 0x7FFFFFFF || !rectified || !count || row_stride < n) return DODT_EINVAL;
+  if (points_dtype != DODT_F32 && points_dtype != DODT_F64) return DODT_EINVAL;
+  const bool filter = image_w > 0 && image_h > 0;
+  if (filter && !p2) return DODT_EINVAL;
+  cudaStream_t stream = as_stream(stream_);
+  if (n == 0) {
+    DODT_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int32_t), stream));
+    return DODT_OK;
+  }
+  if (!velo || !points) return DODT_EINVAL;
+  if (reinterpret_cast<uintptr_t>(velo) % 16 != 0) return DODT_EALIGN;
+  if (!workspace || workspace_bytes < dodt_lidar_workspace_bytes(n)) return DODT_ECAPACITY;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return DODT_EALIGN;
+  char *ws = static_cast<char *>(workspace);
+  const size_t nn = static_cast<size_t>(n);
+  double *cam = reinterpret_cast<double *>(ws);
+  size_t off = 3 * nn * sizeof(double);
+  unsigned char *keep = reinterpret_cast<unsigned char *>(ws + off);
+  off += (nn + 255) & ~static_cast<size_t>(255);
+  int32_t *idx = reinterpret_cast<int32_t *>(ws + off);
+  off = (off + nn * sizeof(int32_t) + 255) & ~static_cast<size_t>(255);
+  void *cws = ws + off;
+  LidarGeom g;
+  for (int k = 0; k < 12; ++k) { g.m[k] = rectified[k]; g.p[k] = p2 ? p2[k] : 0.0; }
+  g.im_w = image_w; g.im_h = image_h; g.filter = filter ? 1 : 0;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  lidar_transform<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(velo), n, g, cam, keep);
+  DODT_AFTER_LAUNCH();
+  const int rc = dodt_compact_mask(keep, n, idx, count, cws, workspace_bytes - off, stream_);
+  if (rc != DODT_OK) return rc;
+  if (points_dtype == DODT_F64)
+    lidar_gather<double><<<blocks, 256, 0, stream>>>(cam, n, idx, count, row_stride, static_cast<double *>(points));
+  else
+    lidar_gather<float><<<blocks, 256, 0, stream>>>(cam, n, idx, count, row_stride, static_cast<float *>(points));
+  DODT_AFTER_LAUNCH();
+  return DODT_OK;
+}
+
+}  // extern "C"

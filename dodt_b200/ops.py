@@ -92,17 +92,18 @@ def bev_workspace_bytes(n_points, num_slices, nx, nz):
     return int(load().dodt_bev_workspace_bytes(int(n_points), int(num_slices), int(nx), int(nz)))
 
 
-def bev_slices(points, params, maps, occ, stats, workspace, winner_idx=None, counts=None):
+def bev_slices(points, params, maps, occ, stats, workspace, winner_idx=None, counts=None,
+               n_dev=None):
     """points (3, N) CUDA f32/f64 with unit inner stride. Fills maps [(S+1), nz, nx] f32,
-    occ [nx, nz] u8 (or None), stats [24] i32."""
-    _need_cuda(points, maps, occ, stats, workspace, winner_idx, counts)
+    occ [nx, nz] u8 (or None), stats [24] i32. n_dev: optional device int32 point count."""
+    _need_cuda(points, maps, occ, stats, workspace, winner_idx, counts, n_dev)
     if points.dim() != 2 or points.shape[0] != 3:
         raise ValueError("Points have the wrong shape: {}".format(tuple(points.shape)))
     n = points.shape[1]
     if n > 0 and points.stride(1) != 1:
         raise ValueError("points rows must be contiguous")
     row_stride = points.stride(0) if n > 0 else 0
-    rc = load().dodt_bev_slices(_ptr(points), _dtype_code(points), n, max(row_stride, n),
+    rc = load().dodt_bev_slices(_ptr(points), _dtype_code(points), n, _ptr(n_dev), max(row_stride, n),
                                 ctypes.byref(params), _ptr(maps), _ptr(occ), _ptr(stats),
                                 _ptr(winner_idx), _ptr(counts), _ptr(workspace),
                                 workspace.numel() * workspace.element_size(), _stream())
@@ -211,6 +212,35 @@ def gather_rows_multi(pairs, idx, count):
         specs[k].width = 1 if src.dim() == 1 else int(src.shape[1])
     check(load().dodt_gather_rows_multi(specs, len(pairs), _ptr(idx), _ptr(count), idx.numel(),
                                         _stream()), "dodt_gather_rows_multi")
+
+
+# ------------------------------------------------------------------------------------------ lidar
+
+
+def lidar_to_camera(velo, rectified, p2=None, im_size=None, dtype=torch.float64, out=None,
+                    count=None, workspace=None):
+    """velo [n, 4] CUDA float32 (KITTI .bin rows) -> (points (3, n) of dtype with the first
+    count[0] columns valid, count [1] int32), both on the device, no synchronisation.
+    rectified: rows 0..2 of R0_rect(4x4).Tr_velo_to_cam(4x4); im_size = [w, h] enables the
+    image-frustum filter of wavedata tracking_utils.get_lidar_point_cloud."""
+    _need_cuda(velo, out, count, workspace)
+    if velo.dim() != 2 or velo.shape[1] != 4 or velo.dtype != torch.float32:
+        raise ValueError("velo must be an [n, 4] float32 tensor (x, y, z, intensity)")
+    velo = velo.contiguous()
+    n = velo.shape[0]
+    dev = velo.device
+    if out is None:
+        out = torch.empty((3, max(n, 1)), dtype=dtype, device=dev)
+    if count is None:
+        count = torch.empty((1,), dtype=torch.int32, device=dev)
+    if workspace is None:
+        workspace = torch.empty(int(load().dodt_lidar_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    w, h = (int(im_size[0]), int(im_size[1])) if im_size is not None else (0, 0)
+    check(load().dodt_lidar_to_camera(_ptr(velo), n, _dbl(np.asarray(rectified)[:3], 12),
+                                      _dbl(p2, 12) if p2 is not None else None, w, h, _ptr(out),
+                                      _dtype_code(out), out.stride(0), _ptr(count), _ptr(workspace),
+                                      workspace.numel(), _stream()), "dodt_lidar_to_camera")
+    return out, count
 
 
 # ------------------------------------------------------------------------------------------ anchors

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DODT_FE_VERSION 105 /* major*100 + minor */
+#define DODT_FE_VERSION 106 /* major*100 + minor */
 
 typedef void *dodt_stream_t; /* cudaStream_t */
 
@@ -111,8 +111,11 @@ size_t dodt_bev_workspace_bytes(int64_t n_points, int32_t num_slices, int32_t nx
  * winner_idx: optional out int32 [num_slices, nz, nx] — index of the winning point per cell
  *             (-1 = empty); NULL to skip (parity/diagnostic output, integer exact).
  * counts    : optional out int32 [nz, nx] — points per cell of the density slice; NULL to skip.
+ * n_dev     : optional device int32 — only the first min(n, *n_dev) points are used (a count
+ *             produced on the device, e.g. by dodt_lidar_to_camera); NULL: all n.
  */
-int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, int64_t row_stride,
+int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, const int32_t *n_dev,
+                    int64_t row_stride,
                     const dodt_bev_params *params /* host */, float *maps, uint8_t *occ,
                     int32_t *stats, int32_t *winner_idx, int32_t *counts, void *workspace,
                     size_t workspace_bytes, dodt_stream_t stream);
@@ -162,6 +165,22 @@ typedef struct dodt_gather_spec {
 int dodt_gather_rows_multi(const dodt_gather_spec *specs /* host */, int32_t n_specs,
                            const int32_t *idx, const int32_t *count, int64_t n_max,
                            dodt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LiDAR ingest in front of S1: wavedata tracking_utils.py:152-203
+ * (get_lidar_point_cloud) = calib_utils.py:484-523 (lidar_to_cam_frame) + the image-frustum filter
+ * through calib_utils.py:394-410 (project_to_image).
+ * velo: device float32 [n, 4] (x, y, z, intensity: the KITTI .bin layout), 16-byte aligned.
+ * rectified: host, rows 0..2 of R0_rect(4x4) . Tr_velo_to_cam(4x4), row-major 3x4; p2: host 3x4.
+ * image_w / image_h > 0: keep points with camera z > 0 whose projection is strictly inside the
+ * image; 0: keep all. points: out (3, *count) structure of arrays of points_dtype, row r at
+ * points + r*row_stride, input order kept; count: out device int32.
+ * ---------------------------------------------------------------------------------------- */
+size_t dodt_lidar_workspace_bytes(int64_t n);
+int dodt_lidar_to_camera(const float *velo, int64_t n, const double rectified[12],
+                         const double p2[12], int32_t image_w, int32_t image_h, void *points,
+                         int32_t points_dtype, int64_t row_stride, int32_t *count, void *workspace,
+                         size_t workspace_bytes, dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Anchor geometry between the stages — host NumPy in the reference.

@@ -12,6 +12,9 @@ Fixtures
         BevSlices.generate_bev (6 maps, stored sparse), the leaf layout of the 0.2-2.0 m slice
         (kitti_utils.create_sliced_voxel_grid_2d) and get_empty_anchor_filter_2d on the 89 600 Car
         anchors (GridAnchor3dGenerator + box_3d_to_anchor).
+  lidar_kitti_000003.npz         raw velodyne scan + calibration matrices of that frame, the
+        frustum-cropped cloud wavedata tracking_utils.get_lidar_point_cloud makes of it and every
+        7th point of the uncropped camera-frame cloud.
   s1s2_synth.npz                 the same on a 30 k-point synthetic cloud incl. degenerate slices.
   s1_unit_vectors.npz            outputs of the reference's own unit-test inputs
         (voxel_grid_2d_test.py, integral_image_2d_test.py, kitti_utils_test.py, obj_utils_test.py).
@@ -72,6 +75,23 @@ def kitti_frames():
         out = reference_s1s2(np.asarray(pc, dtype=np.float64))
         np.savez_compressed(os.path.join(OUT, "s1s2_kitti_%s.npz" % name), **out)
         print("kitti", name, pc.shape, "kept", int(np.unpackbits(out["keep_packed"])[:89600].sum()))
+
+
+def lidar_frame():
+    """Raw velodyne scan + calibration of one fixture frame and what the reference makes of it."""
+    from wavedata.tools.core import calib_utils
+    from wavedata.tools.obj_detection import tracking_utils
+    base = os.path.join(ref_shim.REFERENCE_ROOT, "avod/tests/datasets/Kitti/tracking/training")
+    name = "000003"
+    calib = calib_utils.read_tracking_calibration(base + "/calib", 0)
+    x, y, z, i = calib_utils.read_lidar(base + "/velodyne/0000", 3)
+    velo = np.stack([x, y, z, i], axis=1).astype(np.float32)
+    fov = tracking_utils.get_lidar_point_cloud(name, base + "/calib", base + "/velodyne", im_size=[1242, 375])
+    full = tracking_utils.get_lidar_point_cloud(name, base + "/calib", base + "/velodyne")
+    np.savez_compressed(os.path.join(OUT, "lidar_kitti_000003.npz"), velo=velo, p2=calib.p2,
+                        r0_rect=calib.r0_rect, tr_velodyne_to_cam=calib.tr_velodyne_to_cam,
+                        fov=np.asarray(fov), full_every_7th=np.asarray(full)[:, ::7], im_size=np.array([1242, 375]))
+    print("lidar", velo.shape, "->", np.asarray(fov).shape)
 
 
 def synth_frame():
@@ -182,6 +202,7 @@ if __name__ == "__main__":
     assert ref_shim.install(), "the reference checkout is needed to generate golden vectors"
     os.makedirs(OUT, exist_ok=True)
     kitti_frames()
+    lidar_frame()
     synth_frame()
     unit_vectors()
     independent_tf_ops()

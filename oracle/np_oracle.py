@@ -5,6 +5,7 @@ import this module; nothing under dodt_b200/ does. It restates in NumPy what the
 computes for each stage, each function citing the reference file:line it follows (paths relative
 to the Guoxs/DODT checkout):
 
+  (ingest) lidar_to_cam_frame / lidar_in_camera_view   (wavedata calib_utils / tracking_utils)
   S1  bev_slices / voxelize_2d / point_filter / dist_to_plane / density
   S2  integral_image_2d / map_to_index / empty_anchor_filter_2d
   S3  crop_and_resize       (TensorFlow 1.3.0 core/kernels/crop_and_resize_op.cc — NOT vendored
@@ -29,6 +30,36 @@ Pinning status
           whose outputs are frozen in tests/golden/, and box_list_ops_test.py:86-98's IoU vectors.
 """
 import numpy as np
+
+# ------------------------------------------------------------------------------------------
+# LiDAR ingest (SURVEY 8(f) rank 2)
+# ------------------------------------------------------------------------------------------
+
+
+def lidar_to_cam_frame(xyz_lidar, r0_rect, tr_velodyne_to_cam):
+    """wavedata/wavedata/tools/core/calib_utils.py:484-523: N x 3 lidar -> N x 3 rectified camera."""
+    r0 = np.pad(np.asarray(r0_rect, dtype=np.float64), ((0, 1), (0, 1)), 'constant')
+    r0[3, 3] = 1
+    tf = np.pad(np.asarray(tr_velodyne_to_cam, dtype=np.float64), ((0, 1), (0, 0)), 'constant')
+    tf[3, 3] = 1
+    xyz1 = np.append(xyz_lidar, np.ones(len(xyz_lidar)).reshape(-1, 1), axis=1)
+    return np.dot(np.dot(r0, tf), xyz1.T)[0:3].T
+
+
+def lidar_in_camera_view(velo, r0_rect, tr_velodyne_to_cam, p2, im_size=None):
+    """wavedata/wavedata/tools/obj_detection/tracking_utils.py:152-203 (get_lidar_point_cloud) on
+    an already loaded scan: velo N x 4 (x, y, z, intensity) -> (3, M) camera-frame points that lie
+    in front of the camera and project strictly inside an image of im_size = [w, h]."""
+    pts = lidar_to_cam_frame(np.asarray(velo)[:, :3], r0_rect, tr_velodyne_to_cam)
+    if not im_size:
+        return pts.T
+    pts = pts[pts[:, 2] > 0]
+    pc = pts.T
+    uvw = np.dot(np.asarray(p2), np.append(pc, np.ones((1, pc.shape[1])), axis=0))   # calib_utils.py:394-410
+    u, v = uvw[0] / uvw[2], uvw[1] / uvw[2]
+    keep = (u > 0) & (u < im_size[0]) & (v > 0) & (v < im_size[1])
+    return pts[keep].T
+
 
 # ------------------------------------------------------------------------------------------
 # S1

@@ -304,3 +304,16 @@ def test_c_oracle_matches_numpy_oracle_s5():
     for max_out, thr in ((1024, 0.8), (100, 0.01), (300, 0.5)):
         np.testing.assert_array_equal(CO.non_max_suppression(boxes, scores, max_out, thr),
                                       O.non_max_suppression(boxes, scores, max_out, thr))
+
+
+def test_lidar_ingest_against_reference_outputs():
+    """The reference's get_lidar_point_cloud on a real KITTI tracking scan (frozen by
+    oracle/make_golden.py) == the oracle restatement: same points kept, same order, same float64
+    coordinates (same NumPy, same BLAS)."""
+    g = _load("lidar_kitti_000003.npz")
+    fov = O.lidar_in_camera_view(g["velo"], g["r0_rect"], g["tr_velodyne_to_cam"], g["p2"], list(g["im_size"]))
+    assert fov.shape == g["fov"].shape == (3, 20583)
+    np.testing.assert_allclose(fov, g["fov"], rtol=1e-13, atol=1e-13)
+    full = O.lidar_in_camera_view(g["velo"], g["r0_rect"], g["tr_velodyne_to_cam"], g["p2"])
+    np.testing.assert_allclose(full[:, ::7], g["full_every_7th"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_array_equal(g["fov"], _load("s1s2_kitti_000003.npz")["points"])
