@@ -262,7 +262,7 @@ struct CorrAsyncGeom {
 // shared-memory float; PX = 2: 512 threads (16 warps), 50 accumulators, 6.7 FMAs per float.
 // NST: stages of the cp.async ring (unit u lives in stage u % NST and is requested NST-1 units
 // ahead of its use).
-template <int R, int PX, int FRONT, int TH, int CTAS, int NST>
+template <int R, int PX, int FRONT, int TH, int CTAS, int NST, int DBG = 0>
 __global__ void __launch_bounds__(kTW / (2 * PX) * 2 * TH, CTAS)
 corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const CorrAsyncGeom g,
               float *__restrict__ out) {
@@ -330,7 +330,7 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     for (int k = 0; k < kPiecesPerSlice; ++k) {
       const int idx = slice * kPiecesPerSlice + k;
       const int rr = idx / kPiecesPerRow, j = idx % kPiecesPerRow;
-      if (rr < kRowsPerThread) {
+      if (rr < kRowsPerThread && !(DBG & 2)) {
         if (lx + 16 * j < l_pieces[rr]) {
           const bool ok = static_cast<unsigned>(l_gx0[rr] + 8 * j) < static_cast<unsigned>(g.W);
           const int bytes = ok ? 16 : 0;
@@ -381,6 +381,13 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
       const float *sb = sa + Cfg::A_BYTES / 4;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
+        if (DBG & 1) {   // diagnostic: no shared-memory reads, no FMAs; the copies still ride along
+#pragma unroll
+          for (int p = 0; p < WN; ++p)
+            if (more) issue_slice(half * WN + p);
+          if (half == 0) acc[0][0] += sa[threadIdx.x];
+          continue;
+        }
         float4 va[PX];
 #pragma unroll
         for (int j = 0; j < PX; ++j)
@@ -449,7 +456,7 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     float *gout = out + ((static_cast<size_t>(n) * g.out_h + ty * TH) * g.out_w + tx * kTW) * D2;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 8 == 0) && ((g.out_w * D2) % 2 == 0) &&
                         (valid_floats % 2 == 0);
-    for (int r = warp; r < valid_rows; r += kWarps) {
+    for (int r = warp; r < ((DBG & 4) ? 0 : valid_rows); r += kWarps) {
       const float *src = stg + r * Cfg::OUT_PITCH;
       float *dstrow = gout + static_cast<size_t>(r) * g.out_w * D2;
       if (vec_ok) {
@@ -524,7 +531,7 @@ int launch(const float *a, const float *b, int N, int H, int W, int C, int out_h
   return DODT_OK;
 }
 
-template <int R, int PX, int FRONT, int TH = kTH, int CTAS = 1, int NST = 2>
+template <int R, int PX, int FRONT, int TH = kTH, int CTAS = 1, int NST = 2, int DBG = 0>
 int launch_async(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w,
                  int shift, float *out, int max_ctas, cudaStream_t stream) {
   using Cfg = TmaCfg<R, TH>;
@@ -533,7 +540,7 @@ int launch_async(const float *a, const float *b, int N, int H, int W, int C, int
   static_assert(NST == 2 || Cfg::SPARE == 0, "the staging spare region is laid out for two stages");
   static bool attr_set = false;
   if (!attr_set) {
-    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R, PX, FRONT, TH, CTAS, NST>,
+    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R, PX, FRONT, TH, CTAS, NST, DBG>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
@@ -546,7 +553,7 @@ int launch_async(const float *a, const float *b, int N, int H, int W, int C, int
   g.inv_c = 1.0f / static_cast<float>(C);
   int grid = g.n_tiles < CTAS * kNumSMs ? g.n_tiles : CTAS * kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;   // persistent CTAs: any count works
-  corr_async_k1<R, PX, FRONT, TH, CTAS, NST><<<grid, kThr, smem_bytes, stream>>>(a, b, g, out);
+  corr_async_k1<R, PX, FRONT, TH, CTAS, NST, DBG><<<grid, kThr, smem_bytes, stream>>>(a, b, g, out);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }
@@ -599,6 +606,15 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
       case 2: return launch_async<2, 4, 0>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
       default: return 1;
     }
+  }
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("DODT_CORR_DBG"); dbg = e ? atoi(e) : 0; }
+    if (r == 2 && dbg == 1) return launch_async<2, 4, 0, 8, 2, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+    if (r == 2 && dbg == 2) return launch_async<2, 4, 0, 8, 2, 2, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+    if (r == 2 && dbg == 4) return launch_async<2, 4, 0, 8, 2, 2, 4>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+    if (r == 2 && dbg == 5) return launch_async<2, 4, 0, 8, 2, 2, 5>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+    if (r == 2 && dbg == 6) return launch_async<2, 4, 0, 8, 2, 2, 6>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
   }
   // default: 8-row tiles, 4 warps per CTA, TWO CTAs per SM — the per-unit barrier, the exposed
   // tail of the copies and the epilogue of one CTA hide behind the other CTA's math
