@@ -12,7 +12,13 @@ from dodt_b200.frontend import FrontEnd, HostFrame  # noqa: E402
 
 n_slots = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
-fe = FrontEnd()
+from dodt_b200.frontend import FrontEndConfig  # noqa: E402
+cfg = FrontEndConfig()
+if os.environ.get("ABL_CORR_CTAS"):
+    cfg.corr_max_ctas = int(os.environ["ABL_CORR_CTAS"])
+if os.environ.get("ABL_NMS_WINDOWS"):
+    cfg.nms_max_windows = int(os.environ["ABL_NMS_WINDOWS"])
+fe = FrontEnd(cfg)
 slots = [fe.new_slot() for _ in range(n_slots)]
 for i, s in enumerate(slots):
     HostFrame(fe).fill(synth.frame_inputs(2, i)).upload(s)
