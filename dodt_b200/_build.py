@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(HERE, "libdodt_fe.so")
 
-SOURCES = ["common.cu", "bev_slices.cu", "anchor_filter.cu", "crop_resize.cu", "correlation.cu", "correlation_tma.cu",
+SOURCES = ["common.cu", "bev_slices.cu", "anchor_filter.cu", "crop_resize.cu", "correlation.cu", "correlation_tma.cu", "correlation_grad.cu",
            "nms.cu", "frontend.cu", "anchors.cu", "lidar.cu"]
 
 NVCC_FLAGS = [

@@ -102,6 +102,10 @@ SIGNATURES = {
     "dodt_correlation_shared": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                         c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                         c_void_p]),
+    "dodt_correlation_grad_workspace_bytes": (c_size_t, [c_int32] * 9),
+    "dodt_correlation_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                      c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]),
     "dodt_nms_workspace_bytes": (c_size_t, [c_int64]),
     "dodt_nms_state_offset": (c_size_t, [c_int64]),
     "dodt_nms": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_float, c_int32, c_int32,

@@ -1,0 +1,378 @@
+// S4 backward — gradients of the FlowNet-style correlation with respect to
+// both NHWC float32 inputs, sm_100a.
+//
+// Replaces the reference's TensorFlow custom op "CorrelationGrad" (paths relative to the
+// Guoxs/DODT checkout):
+//   avod/core/corr_layers/correlation.py:30-48                 @tf.RegisterGradient("Correlation")
+//   avod/core/ops/correlation/correlation_grad_kernel.cc:28-151 shape math, two padded temporaries
+//   avod/core/ops/correlation/correlation_grad_kernel.cu.cc:20-107  CorrelateDataBackward0 (d/dA)
+//   avod/core/ops/correlation/correlation_grad_kernel.cu.cc:109-189 CorrelateDataBackward1 (d/dB)
+//
+// With kr = (ks-1)/2, Y = y + pad, X = x + pad (padded coordinates of input pixel (y, x)),
+// s2p = p*s2, s2o = o*s2, k = (p+r)*Wn + (o+r):
+//   gA[n,y,x,c] = 1/(ks^2 C) * sum_{p,o} Bpad[n, Y+s2p, X+s2o, c] * sum_{(oy,ox) in win(Y,X)}     G[n,oy,ox,k]
+//   gB[n,y,x,c] = 1/(ks^2 C) * sum_{p,o} Apad[n, Y-s2p, X-s2o, c] * sum_{(oy,ox) in win(Y-s2p,X-s2o)} G[n,oy,ox,k]
+//   win(Y,X) = output pixels whose ks x ks patch covers (Y,X):
+//              ceil((Y - 2kr - md)/s1) <= oy <= floor((Y - md)/s1), clamped to the output.
+// The padded temporaries are never materialised: taps outside the image are zero. (The reference
+// reads its padded copies without bounds checks, so parameters that push a displaced tap outside
+// the PADDED image are undefined there; here those taps are zero as well.)
+//
+// Kernels
+//   corr_grad_generic<WHICH>  any parameters: one thread per (pixel, channel), the reference's
+//                             loops in the reference's order.
+//   corr_grad_k1<R, REV>      the DODT family (kernel_size 1, stride_1 1, stride_2 2, C % 8 == 0,
+//                             r in {1,2}). The reduction runs over displacements, not channels, so
+//                             the structure mirrors the forward kernel with the roles swapped: a
+//                             thread owns 4 pixels spaced 2 apart on one row and keeps their
+//                             4 x (2r+1)^2 gradient coefficients in REGISTERS for the whole tile
+//                             (staged once through shared memory so that the global reads are
+//                             coalesced), streams 8-channel chunks of the other input (tile + halo)
+//                             through shared memory, and writes 4 x 8 finished gradients per chunk.
+//                             Every value of the other input is read from HBM once per tile
+//                             (halo re-reads hit L2) instead of (2r+1)^2 times.
+//   corr_grad_flip<R>         gB as the same contraction: Gf[n,y,x,k'] = G[n, y+2p'-shift,
+//                             x+2o'-shift, D2-1-k'] (shared-memory staged permutation), then
+//                             gB = corr_grad_k1<R, REV=true>(Gf, A): REV walks the displacements
+//                             backwards, which is the reference's summation order for gB, so both
+//                             gradients are bit-identical to a scalar restatement that uses fmaf.
+//
+// Algorithmic HBM bytes (both gradients, 700x800x32, 25 displacements): read G 56 MB + A, B 2 x 71.68
+// MB, write gA, gB 2 x 71.68 MB = 342.7 MB; the flip pass adds 2 x 70 MB of workspace traffic.
+#include "common.cuh"
+
+namespace dodt {
+namespace {
+
+struct GradGeom {
+  int batch, H, W, C;
+  int ks, kr, md, s1, s2, pad;
+  int out_h, out_w, out_c;
+  int r, wn;
+};
+
+// floor / ceil of a / b for b > 0 and any sign of a (the reference's ROUND_OFF trick,
+// correlation_grad_kernel.cu.cc:47-62, computes exactly these)
+__device__ __forceinline__ int floor_div(int a, int b) {
+  const int q = a / b;
+  return (a % b != 0 && (a < 0)) ? q - 1 : q;
+}
+__device__ __forceinline__ int ceil_div_s(int a, int b) { return -floor_div(-a, b); }
+
+// WHICH = 0: gradient w.r.t. input_a (other = input_b); 1: w.r.t. input_b (other = input_a)
+template <int WHICH>
+__global__ void __launch_bounds__(256)
+corr_grad_generic(const float *__restrict__ grad, const float *__restrict__ other, GradGeom g,
+                  long long total, float *__restrict__ dst) {
+  const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (t >= total) return;
+  const int c = static_cast<int>(t % g.C);
+  long long rr = t / g.C;
+  const int x = static_cast<int>(rr % g.W);
+  rr /= g.W;
+  const int y = static_cast<int>(rr % g.H);
+  const int n = static_cast<int>(rr / g.H);
+  const int X = x + g.pad, Y = y + g.pad;
+  const float *gn = grad + static_cast<size_t>(n) * g.out_h * g.out_w * g.out_c;
+  const float *on = other + static_cast<size_t>(n) * g.H * g.W * g.C;
+
+  float sum = 0.0f;
+  for (int p = -g.r; p <= g.r; ++p)
+    for (int o = -g.r; o <= g.r; ++o) {
+      const int s2o = g.s2 * o, s2p = g.s2 * p;
+      // WHICH 0: window of (Y, X), tap Bpad[Y+s2p, X+s2o]; WHICH 1: window and tap at (Y-s2p, X-s2o)
+      const int wy = WHICH == 0 ? Y : Y - s2p, wx = WHICH == 0 ? X : X - s2o;
+      const int ty = WHICH == 0 ? Y + s2p : Y - s2p, tx = WHICH == 0 ? X + s2o : X - s2o;
+      int xmin = ceil_div_s(wx - 2 * g.kr - g.md, g.s1), xmax = floor_div(wx - g.md, g.s1);
+      int ymin = ceil_div_s(wy - 2 * g.kr - g.md, g.s1), ymax = floor_div(wy - g.md, g.s1);
+      if (!(xmax >= 0 && ymax >= 0 && xmin <= g.out_w - 1 && ymin <= g.out_h - 1)) continue;
+      xmin = max(0, xmin); xmax = min(g.out_w - 1, xmax);
+      ymin = max(0, ymin); ymax = min(g.out_h - 1, ymax);
+      const int uy = ty - g.pad, ux = tx - g.pad;      // unpadded tap
+      float v = 0.0f;
+      if (uy >= 0 && uy < g.H && ux >= 0 && ux < g.W)
+        v = __ldg(on + (static_cast<size_t>(uy) * g.W + ux) * g.C + c);
+      const int op = (p + g.r) * g.wn + (o + g.r);
+      for (int oy = ymin; oy <= ymax; ++oy)
+        for (int ox = xmin; ox <= xmax; ++ox)
+          sum = fmaf(__ldg(gn + (static_cast<size_t>(oy) * g.out_w + ox) * g.out_c + op), v, sum);
+    }
+  const float sumelems = static_cast<float>(g.ks * g.ks * g.C);
+  dst[t] = __fdiv_rn(sum, sumelems);
+}
+
+// ---------------------------------------------------------------------------------------------
+// DODT family: kernel_size 1, stride_1 1, stride_2 2.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTW = 64, kTH = 8, kPX = 4, kCC = 8;
+constexpr int kThreads = kTW / (2 * kPX) * 2 * kTH;   // 128
+
+// 32-byte pixel vectors; the two 16-byte halves of pixel p swap when bit 2 of p is set (as in the
+// forward kernel: eight lanes reading eight different pixels hit eight different bank groups)
+__device__ __forceinline__ int smem_off(int pixel, int half) {
+  return pixel * kCC + ((half ^ ((pixel >> 2) & 1)) << 2);
+}
+
+template <int R>
+struct GradCfg {
+  static constexpr int WN = 2 * R + 1, D2 = WN * WN, HALO = 2 * R;
+  static constexpr int BW = kTW + 2 * HALO;
+  static constexpr int BPITCH = ((BW + 7) / 8) * 8 + 2;       // 2 (mod 8) pixels
+  static constexpr int BH = kTH + 2 * HALO;
+  static constexpr int G_PITCH = kTW * D2 + ((2 - kTW * D2 % 32) + 32) % 32;  // 2 (mod 32) floats
+  static constexpr int G_FLOATS = kTH * G_PITCH;
+  static constexpr int B_FLOATS = BH * BPITCH * kCC;
+  static constexpr size_t SMEM = static_cast<size_t>(G_FLOATS + B_FLOATS) * sizeof(float);
+};
+
+// coef [batch, ch, cw, D2]: ch x cw is the extent of the coefficient map; input pixel (y, x) uses
+// coef[y - cshift, x - cshift] (zero outside). other/dst [batch, H, W, C].
+//   dst[n,y,x,c] = 1/C * sum_{p,o} coef[n, y-cshift, x-cshift, k] * other[n, y+2p, x+2o, c]
+// REV: walk k = D2-1 .. 0 instead of 0 .. D2-1.
+template <int R, bool REV>
+__global__ void __launch_bounds__(kThreads, 2)
+corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, int batch, int H, int W,
+             int C, int ch, int cw, int cshift, int tiles_x, int tiles_y, float *__restrict__ dst) {
+  using Cfg = GradCfg<R>;
+  constexpr int WN = Cfg::WN, D2 = Cfg::D2, NB = kPX + 2 * R;
+  extern __shared__ __align__(16) float smem[];
+  float *sg = smem;                     // [kTH][G_PITCH]
+  float *sb = smem + Cfg::G_FLOATS;     // [BH][BPITCH][kCC]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // lane bits: [0] parity, [1..2] row & 3, [3..4] group & 3; warps tile 2 (rows) x 2 (x halves)
+  const int row = (warp >> 1) * 4 + ((lane >> 1) & 3);
+  const int x0 = ((warp & 1) * 4 + (lane >> 3)) * (2 * kPX) + (lane & 1);
+  const float sumelems = static_cast<float>(C);
+  const int n_tiles = tiles_x * tiles_y * batch;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tx0 = (tile % tiles_x) * kTW;
+    const int ty0 = ((tile / tiles_x) % tiles_y) * kTH;
+    const int n = tile / (tiles_x * tiles_y);
+    const float *cn = coef + static_cast<size_t>(n) * ch * cw * D2;
+    const float *on = other + static_cast<size_t>(n) * H * W * C;
+    float *dn = dst + static_cast<size_t>(n) * H * W * C;
+
+    __syncthreads();   // previous tile finished with sg / sb
+    // ---- coefficients of the tile: rows are contiguous runs of kTW * D2 floats
+    for (int e = threadIdx.x; e < kTH * kTW * D2; e += kThreads) {
+      const int r_ = e / (kTW * D2), f = e % (kTW * D2);
+      const int gy = ty0 + r_ - cshift, gx = tx0 + f / D2 - cshift;
+      float v = 0.0f;
+      if (gy >= 0 && gy < ch && gx >= 0 && gx < cw)
+        v = __ldg(cn + (static_cast<size_t>(gy) * cw + gx) * D2 + f % D2);
+      sg[r_ * Cfg::G_PITCH + f] = v;
+    }
+    __syncthreads();
+    float gk[kPX][D2];
+#pragma unroll
+    for (int j = 0; j < kPX; ++j)
+#pragma unroll
+      for (int k = 0; k < D2; ++k) gk[j][k] = sg[row * Cfg::G_PITCH + (x0 + 2 * j) * D2 + k];
+
+    for (int c0 = 0; c0 < C; c0 += kCC) {
+      __syncthreads();
+      // ---- stage the other input's tile with its halo (zero outside the image = padding)
+      for (int e = threadIdx.x; e < Cfg::BH * Cfg::BW * 2; e += kThreads) {
+        const int half = e & 1, p = e >> 1;
+        const int py = p / Cfg::BW, px = p % Cfg::BW;
+        const int gy = ty0 + py - Cfg::HALO, gx = tx0 + px - Cfg::HALO;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+          v = __ldg(reinterpret_cast<const float4 *>(on + (static_cast<size_t>(gy) * W + gx) * C + c0) + half);
+        *reinterpret_cast<float4 *>(sb + smem_off(py * Cfg::BPITCH + px, half)) = v;
+      }
+      __syncthreads();
+
+      float4 acc[kPX][2];
+#pragma unroll
+      for (int j = 0; j < kPX; ++j) acc[j][0] = acc[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int pi = 0; pi < WN; ++pi) {
+        const int p = REV ? WN - 1 - pi : pi;
+        float4 vb[NB][2];
+#pragma unroll
+        for (int q = 0; q < NB; ++q)
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+            vb[q][half] = *reinterpret_cast<const float4 *>(
+                sb + smem_off((row + 2 * p) * Cfg::BPITCH + x0 + 2 * q, half));
+#pragma unroll
+        for (int oi = 0; oi < WN; ++oi) {
+          const int o = REV ? WN - 1 - oi : oi;
+#pragma unroll
+          for (int j = 0; j < kPX; ++j) {
+            const float w = gk[j][p * WN + o];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              acc[j][half].x = fmaf(w, vb[j + o][half].x, acc[j][half].x);
+              acc[j][half].y = fmaf(w, vb[j + o][half].y, acc[j][half].y);
+              acc[j][half].z = fmaf(w, vb[j + o][half].z, acc[j][half].z);
+              acc[j][half].w = fmaf(w, vb[j + o][half].w, acc[j][half].w);
+            }
+          }
+        }
+      }
+      const int oy = ty0 + row;
+      if (oy < H) {
+#pragma unroll
+        for (int j = 0; j < kPX; ++j) {
+          const int ox = tx0 + x0 + 2 * j;
+          if (ox < W) {
+            float4 *d = reinterpret_cast<float4 *>(dn + (static_cast<size_t>(oy) * W + ox) * C + c0);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              float4 v = acc[j][half];
+              v.x = __fdiv_rn(v.x, sumelems); v.y = __fdiv_rn(v.y, sumelems);
+              v.z = __fdiv_rn(v.z, sumelems); v.w = __fdiv_rn(v.w, sumelems);
+              d[half] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// Gf[n,y,x,k'] = G[n, y + 2p' - shift, x + 2o' - shift, D2-1-k'] for input pixel (y,x) in H x W,
+// k' = (p'+R)*WN + (o'+R); zero where the source lies outside the out_h x out_w gradient map.
+// A CTA produces an FT_H x FT_W tile: the source tile with its halo is read in contiguous rows
+// into shared memory, the permuted tile is written in contiguous rows.
+constexpr int kFH = 8, kFW = 32, kFlipThreads = 256;
+template <int R>
+__global__ void __launch_bounds__(kFlipThreads)
+corr_grad_flip(const float *__restrict__ grad, int out_h, int out_w, int H, int W, int shift,
+               float *__restrict__ gf) {
+  constexpr int WN = 2 * R + 1, D2 = WN * WN, HALO = 2 * R;
+  constexpr int SW = kFW + 2 * HALO, SH = kFH + 2 * HALO;
+  constexpr int PITCH = SW * D2 + 1;
+  extern __shared__ __align__(16) float smem[];
+  const int n = blockIdx.z, ty0 = blockIdx.y * kFH, tx0 = blockIdx.x * kFW;
+  const float *gn = grad + static_cast<size_t>(n) * out_h * out_w * D2;
+  float *fn = gf + static_cast<size_t>(n) * H * W * D2;
+  for (int e = threadIdx.x; e < SH * SW * D2; e += kFlipThreads) {
+    const int r_ = e / (SW * D2), f = e % (SW * D2);
+    const int gy = ty0 + r_ - HALO - shift, gx = tx0 + f / D2 - HALO - shift;
+    float v = 0.0f;
+    if (gy >= 0 && gy < out_h && gx >= 0 && gx < out_w)
+      v = __ldg(gn + (static_cast<size_t>(gy) * out_w + gx) * D2 + f % D2);
+    smem[r_ * PITCH + f] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kFH * kFW * D2; e += kFlipThreads) {
+    const int r_ = e / (kFW * D2), f = e % (kFW * D2);
+    const int px = f / D2, k = f % D2;
+    const int y = ty0 + r_, x = tx0 + px;
+    if (y >= H || x >= W) continue;
+    const int p = k / WN, o = k % WN;   // p' + R, o' + R
+    fn[(static_cast<size_t>(y) * W + x) * D2 + k] =
+        smem[(r_ + 2 * p) * PITCH + (px + 2 * o) * D2 + (D2 - 1 - k)];
+  }
+}
+
+template <int R>
+int launch_k1(const float *grad, const float *a, const float *b, const GradGeom &g, float *ga,
+              float *gb, float *ws, cudaStream_t stream) {
+  using Cfg = GradCfg<R>;
+  const int shift = g.md - g.pad;
+  const int tiles_x = ceil_div(g.W, kTW), tiles_y = ceil_div(g.H, kTH);
+  const long long n_tiles = static_cast<long long>(tiles_x) * tiles_y * g.batch;
+  if (n_tiles > 0x7FFFFFFFll) return 1;
+  const int grid = static_cast<int>(n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs);
+  DODT_CUDA_TRY(cudaFuncSetAttribute(corr_grad_k1<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(Cfg::SMEM)));
+  DODT_CUDA_TRY(cudaFuncSetAttribute(corr_grad_k1<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(Cfg::SMEM)));
+  if (ga) {
+    corr_grad_k1<R, false><<<grid, kThreads, Cfg::SMEM, stream>>>(
+        grad, b, g.batch, g.H, g.W, g.C, g.out_h, g.out_w, shift, tiles_x, tiles_y, ga);
+    DODT_AFTER_LAUNCH();
+  }
+  if (gb) {
+    constexpr int D2 = Cfg::D2, HALO = Cfg::HALO;
+    const size_t fsmem = (static_cast<size_t>(kFH + 2 * HALO) * ((kFW + 2 * HALO) * D2 + 1)) * sizeof(float);
+    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_grad_flip<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(fsmem)));
+    dim3 fgrid(ceil_div(g.W, kFW), ceil_div(g.H, kFH), g.batch);
+    corr_grad_flip<R><<<fgrid, kFlipThreads, fsmem, stream>>>(grad, g.out_h, g.out_w, g.H, g.W, shift, ws);
+    DODT_AFTER_LAUNCH();
+    corr_grad_k1<R, true><<<grid, kThreads, Cfg::SMEM, stream>>>(
+        ws, a, g.batch, g.H, g.W, g.C, g.H, g.W, 0, tiles_x, tiles_y, gb);
+    DODT_AFTER_LAUNCH();
+  }
+  return DODT_OK;
+}
+
+bool k1_family(const GradGeom &g) {
+  return g.ks == 1 && g.s1 == 1 && g.s2 == 2 && (g.r == 1 || g.r == 2) && g.C % kCC == 0 &&
+         g.batch <= 65535;
+}
+
+int fill(int32_t batch, int32_t H, int32_t W, int32_t C, int32_t ks, int32_t md, int32_t s1,
+         int32_t s2, int32_t pad, GradGeom *g) {
+  if (batch <= 0 || H <= 0 || W <= 0 || C <= 0 || ks <= 0 || md < 0 || s1 <= 0 || s2 <= 0 || pad < 0)
+    return DODT_EINVAL;
+  int32_t hwc[3];
+  const int rc = dodt_correlation_out_shape(H, W, ks, md, s1, s2, pad, hwc);  // odd ks, fits
+  if (rc != DODT_OK) return rc;
+  g->batch = batch; g->H = H; g->W = W; g->C = C;
+  g->ks = ks; g->kr = (ks - 1) / 2; g->md = md; g->s1 = s1; g->s2 = s2; g->pad = pad;
+  g->out_h = hwc[0]; g->out_w = hwc[1]; g->out_c = hwc[2];
+  g->r = md / s2; g->wn = 2 * g->r + 1;
+  return DODT_OK;
+}
+
+}  // namespace
+}  // namespace dodt
+
+extern "C" {
+
+size_t dodt_correlation_grad_workspace_bytes(int32_t batch, int32_t height, int32_t width,
+                                             int32_t channels, int32_t kernel_size,
+                                             int32_t max_displacement, int32_t stride_1,
+                                             int32_t stride_2, int32_t pad) {
+  dodt::GradGeom g;
+  if (dodt::fill(batch, height, width, channels, kernel_size, max_displacement, stride_1, stride_2,
+                 pad, &g) != DODT_OK)
+    return 0;
+  if (!dodt::k1_family(g)) return 0;
+  return static_cast<size_t>(g.batch) * g.H * g.W * g.out_c * sizeof(float);
+}
+
+int dodt_correlation_grad(const float *grad, const float *a, const float *b, int32_t batch,
+                          int32_t height, int32_t width, int32_t channels, int32_t kernel_size,
+                          int32_t max_displacement, int32_t stride_1, int32_t stride_2, int32_t pad,
+                          float *grad_a, float *grad_b, void *workspace, size_t workspace_bytes,
+                          dodt_stream_t stream_) {
+  using namespace dodt;
+  if (!grad || !a || !b || (!grad_a && !grad_b)) return DODT_EINVAL;
+  GradGeom g;
+  const int rc = fill(batch, height, width, channels, kernel_size, max_displacement, stride_1,
+                      stride_2, pad, &g);
+  if (rc != DODT_OK) return rc;
+  cudaStream_t stream = as_stream(stream_);
+  auto al16 = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  const size_t need = static_cast<size_t>(g.batch) * g.H * g.W * g.out_c * sizeof(float);
+  if (k1_family(g) && al16(a) && al16(b) && (!grad_a || al16(grad_a)) && (!grad_b || al16(grad_b)) &&
+      (!grad_b || (workspace && workspace_bytes >= need && al16(workspace)))) {
+    int done = 1;
+    float *ws = static_cast<float *>(workspace);
+    if (g.r == 1) done = launch_k1<1>(grad, a, b, g, grad_a, grad_b, ws, stream);
+    if (g.r == 2) done = launch_k1<2>(grad, a, b, g, grad_a, grad_b, ws, stream);
+    if (done <= 0) return done;
+  }
+  const long long total = static_cast<long long>(g.batch) * g.H * g.W * g.C;
+  const long long blocks = (total + 255) / 256;
+  if (blocks > 0x7FFFFFFFll) return DODT_ECAPACITY;
+  if (grad_a) {
+    corr_grad_generic<0><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(grad, b, g, total, grad_a);
+    DODT_AFTER_LAUNCH();
+  }
+  if (grad_b) {
+    corr_grad_generic<1><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(grad, a, g, total, grad_b);
+    DODT_AFTER_LAUNCH();
+  }
+  return DODT_OK;
+}
+
+}  // extern "C"

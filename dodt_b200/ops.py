@@ -453,6 +453,49 @@ def correlation(a, b, kernel_size, max_displacement, stride_1, stride_2, pad, ou
     return out
 
 
+def correlation_grad_workspace_bytes(N, H, W, C, kernel_size, max_displacement, stride_1, stride_2, pad):
+    return int(load().dodt_correlation_grad_workspace_bytes(N, H, W, C, kernel_size, max_displacement,
+                                                             stride_1, stride_2, pad))
+
+
+def correlation_grad(grad, a, b, kernel_size, max_displacement, stride_1, stride_2, pad,
+                     grad_a=None, grad_b=None, workspace=None, need_a=True, need_b=True):
+    """CorrelationGrad (correlation_grad_kernel.cc:28-151): grad [N,oh,ow,oc], a, b [N,H,W,C] f32 ->
+    (grad_a, grad_b) [N,H,W,C]; a gradient that is not needed is returned as None."""
+    _need_cuda(grad, a, b, grad_a, grad_b, workspace)
+    if a.dim() != 4:
+        raise ValueError("input_a must have rank 4")
+    if b.dim() != 4:
+        raise ValueError("input_b must have rank 4")
+    if a.shape != b.shape:
+        raise ValueError("input_a and input_b must have the same shape")
+    if kernel_size % 2 == 0:
+        raise ValueError("kernel_size must be odd")
+    if a.dtype != torch.float32 or b.dtype != torch.float32 or grad.dtype != torch.float32:
+        raise TypeError("correlation_grad expects float32 tensors")
+    a, b, grad = a.contiguous(), b.contiguous(), grad.contiguous()
+    N, H, W, C = a.shape
+    oh, ow, oc = correlation_out_shape(H, W, kernel_size, max_displacement, stride_1, stride_2, pad)
+    if tuple(grad.shape) != (N, oh, ow, oc):
+        raise ValueError("gradients must have the shape of the correlation output %r" % ((N, oh, ow, oc),))
+    if need_a and grad_a is None:
+        grad_a = torch.empty_like(a)
+    if need_b and grad_b is None:
+        grad_b = torch.empty_like(b)
+    ws_bytes = correlation_grad_workspace_bytes(N, H, W, C, kernel_size, max_displacement, stride_1,
+                                                stride_2, pad) if need_b else 0
+    if ws_bytes and workspace is None:
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    check(load().dodt_correlation_grad(_ptr(grad), _ptr(a), _ptr(b), N, H, W, C, kernel_size,
+                                       max_displacement, stride_1, stride_2, pad,
+                                       _ptr(grad_a) if need_a else None,
+                                       _ptr(grad_b) if need_b else None,
+                                       _ptr(workspace) if workspace is not None else None,
+                                       int(workspace.numel() * workspace.element_size()) if workspace is not None else 0,
+                                       _stream()), "dodt_correlation_grad")
+    return (grad_a if need_a else None), (grad_b if need_b else None)
+
+
 # ------------------------------------------------------------------------------------------ S5
 
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DODT_FE_VERSION 106 /* major*100 + minor */
+#define DODT_FE_VERSION 107 /* major*100 + minor */
 
 typedef void *dodt_stream_t; /* cudaStream_t */
 
@@ -291,6 +291,27 @@ int dodt_correlation_shared(const float *a, const float *b, int32_t batch, int32
                             int32_t width, int32_t channels, int32_t kernel_size,
                             int32_t max_displacement, int32_t stride_1, int32_t stride_2,
                             int32_t pad, float *out, int32_t max_ctas, dodt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * S4 backward — gradients of the correlation w.r.t. both inputs. Replaces the
+ * TF custom op "CorrelationGrad": avod/core/corr_layers/correlation.py:30-48
+ * (@tf.RegisterGradient), correlation_grad_kernel.cc:28-151 and correlation_grad_kernel.cu.cc:20-189
+ * (CorrelateDataBackward0 / CorrelateDataBackward1). Same attributes as the forward op.
+ * grad [batch,out_h,out_w,out_c] f32 (the gradient of the forward output), a, b [batch,H,W,C] ->
+ * grad_a, grad_b [batch,H,W,C] (either may be NULL: that gradient is skipped).
+ * workspace: dodt_correlation_grad_workspace_bytes(...) bytes, 16-byte aligned (0 for parameter
+ * sets outside the kernel_size 1 / stride_1 1 / stride_2 2 family, which take the generic kernel;
+ * a missing or short workspace also selects the generic kernel for grad_b).
+ * ---------------------------------------------------------------------------------------- */
+size_t dodt_correlation_grad_workspace_bytes(int32_t batch, int32_t height, int32_t width,
+                                             int32_t channels, int32_t kernel_size,
+                                             int32_t max_displacement, int32_t stride_1,
+                                             int32_t stride_2, int32_t pad);
+int dodt_correlation_grad(const float *grad, const float *a, const float *b, int32_t batch,
+                          int32_t height, int32_t width, int32_t channels, int32_t kernel_size,
+                          int32_t max_displacement, int32_t stride_1, int32_t stride_2, int32_t pad,
+                          float *grad_a, float *grad_b, void *workspace, size_t workspace_bytes,
+                          dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * S5 — tf.image.non_max_suppression (TensorFlow 1.3.0 core/kernels/non_max_suppression_op.cc),

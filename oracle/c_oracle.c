@@ -4,6 +4,9 @@
  * Restates, loop for loop, the three stages whose reference arithmetic is compiled code:
  *   oracle_correlation      avod/core/ops/correlation/correlation_kernel.cu.cc:21-119 on inputs
  *                           padded as pad.cu.cc:14-74 (GPU-only TF op in the reference)
+ *   oracle_correlation_grad avod/core/ops/correlation/correlation_grad_kernel.cu.cc:20-189
+ *                           (CorrelateDataBackward0 / CorrelateDataBackward1), loop for loop,
+ *                           with the multiply-add fused as nvcc's default -fmad=true compiles it
  *   oracle_crop_and_resize  TensorFlow 1.3.0 core/kernels/crop_and_resize_op.cc (CPU functor)
  *   oracle_nms              TensorFlow 1.3.0 core/kernels/non_max_suppression_op.cc
  * Built by oracle/build_oracle.py with gcc -O2 -ffp-contract=off (every fp32 operation rounded
@@ -48,6 +51,59 @@ int oracle_correlation(const float *a, const float *b, int N, int H, int W, int 
           out[(((size_t)n * oh + y) * ow + x) * oc + k] = total / sumelems;
         }
       }
+  return 0;
+}
+
+/* correlation_grad_kernel.cu.cc:47-62: the ROUND_OFF trick is ceil / floor of a signed quotient */
+static int grad_lo(int v, int s1) { return (v + 50000 * s1 - 1) / s1 + 1 - 50000; }
+static int grad_hi(int v, int s1) { return (v + 50000 * s1) / s1 - 50000; }
+
+/* which = 0: d/d input_a (other = input_b, CorrelateDataBackward0, :20-107);
+ * which = 1: d/d input_b (other = input_a, CorrelateDataBackward1, :109-189).
+ * Padded temporaries are not built: a tap outside the image is the zero PadData wrote (or, outside
+ * the padded image, the value this restatement DEFINES as zero; the reference reads out of bounds). */
+static void grad_one(int which, const float *grad, const float *other, int N, int H, int W, int C,
+                     int ks, int md, int s1, int s2, int pad, int oh, int ow, float *dst) {
+  const int kr = (ks - 1) / 2, r = md / s2, wn = 2 * r + 1, oc = wn * wn;
+  const float sumelems = (float)(ks * ks * C);
+  for (int n = 0; n < N; ++n)
+    for (int yy = 0; yy < H; ++yy)
+      for (int xx = 0; xx < W; ++xx)
+        for (int k = 0; k < C; ++k) {
+          const int x = xx + pad, y = yy + pad;
+          float sum = 0.0f;
+          for (int p = -r; p <= r; ++p)
+            for (int o = -r; o <= r; ++o) {
+              const int s2o = s2 * o, s2p = s2 * p;
+              const int wx = which ? x - s2o : x, wy = which ? y - s2p : y;
+              int xmin = grad_lo(wx - 2 * kr - md, s1), ymin = grad_lo(wy - 2 * kr - md, s1);
+              int xmax = grad_hi(wx - md, s1), ymax = grad_hi(wy - md, s1);
+              if (!(xmax >= 0 && ymax >= 0 && xmin <= ow - 1 && ymin <= oh - 1)) continue;
+              if (xmin < 0) xmin = 0;
+              if (xmax > ow - 1) xmax = ow - 1;
+              if (ymin < 0) ymin = 0;
+              if (ymax > oh - 1) ymax = oh - 1;
+              const int ty = (which ? y - s2p : y + s2p) - pad, tx = (which ? x - s2o : x + s2o) - pad;
+              float v = 0.0f;
+              if (ty >= 0 && ty < H && tx >= 0 && tx < W) v = other[(((size_t)n * H + ty) * W + tx) * C + k];
+              const int op = (p + r) * wn + (o + r);
+              for (int gy = ymin; gy <= ymax; ++gy)
+                for (int gx = xmin; gx <= xmax; ++gx)
+                  sum = fmaf(grad[(((size_t)n * oh + gy) * ow + gx) * oc + op], v, sum);
+            }
+          dst[(((size_t)n * H + yy) * W + xx) * C + k] = sum / sumelems;
+        }
+}
+
+int oracle_correlation_grad(const float *grad, const float *a, const float *b, int N, int H, int W,
+                            int C, int ks, int md, int s1, int s2, int pad, float *ga, float *gb) {
+  if (ks % 2 == 0) return -1;
+  const int kr = (ks - 1) / 2, border = md + kr;
+  const int oh = (int)ceilf((float)(H + 2 * pad - 2 * border) / (float)s1);
+  const int ow = (int)ceilf((float)(W + 2 * pad - 2 * border) / (float)s1);
+  if (oh < 1 || ow < 1) return -2;
+  if (ga) grad_one(0, grad, b, N, H, W, C, ks, md, s1, s2, pad, oh, ow, ga);
+  if (gb) grad_one(1, grad, a, N, H, W, C, ks, md, s1, s2, pad, oh, ow, gb);
   return 0;
 }
 

@@ -17,6 +17,8 @@ def _load():
         i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
         lib.oracle_correlation.restype = ctypes.c_int
         lib.oracle_correlation.argtypes = [f32p, f32p] + [ctypes.c_int] * 9 + [f32p]
+        lib.oracle_correlation_grad.restype = ctypes.c_int
+        lib.oracle_correlation_grad.argtypes = [f32p, f32p, f32p] + [ctypes.c_int] * 9 + [f32p, f32p]
         lib.oracle_crop_and_resize.restype = ctypes.c_int
         lib.oracle_crop_and_resize.argtypes = [f32p] + [ctypes.c_int] * 4 + [f32p, i32p, ctypes.c_int,
                                                                           ctypes.c_int, ctypes.c_int,
@@ -39,6 +41,24 @@ def correlation(input_a, input_b, kernel_size=1, max_displacement=20, stride_1=1
                                     stride_2, padding, out)
     assert rc == 0, rc
     return out
+
+
+def correlation_grad(gradients, input_a, input_b, kernel_size=1, max_displacement=20, stride_1=1,
+                     stride_2=2, padding=20):
+    """(backprops_a, backprops_b) of the reference's CorrelationGrad op
+    (avod/core/corr_layers/correlation.py:30-48)."""
+    from .np_oracle import correlation_out_shape
+    a = np.ascontiguousarray(input_a, dtype=np.float32)
+    b = np.ascontiguousarray(input_b, dtype=np.float32)
+    g = np.ascontiguousarray(gradients, dtype=np.float32)
+    N, H, W, C = a.shape
+    assert g.shape == (N,) + correlation_out_shape(H, W, kernel_size, max_displacement, stride_1,
+                                                    stride_2, padding)
+    ga, gb = np.empty_like(a), np.empty_like(b)
+    rc = _load().oracle_correlation_grad(g, a, b, N, H, W, C, kernel_size, max_displacement,
+                                         stride_1, stride_2, padding, ga, gb)
+    assert rc == 0, rc
+    return ga, gb
 
 
 def crop_and_resize(image, boxes, box_ind, crop_size, extrapolation_value=0.0):
