@@ -21,7 +21,7 @@
 // Kernels
 //   corr_grad_generic<WHICH>  any parameters: one thread per (pixel, channel), the reference's
 //                             loops in the reference's order.
-//   corr_grad_k1<R, REV>      the DODT family (kernel_size 1, stride_1 1, stride_2 2, C % 8 == 0,
+//   corr_grad_k1<R, REV, GB>  the DODT family (kernel_size 1, stride_1 1, stride_2 2, C % 8 == 0,
 //                             r in {1,2}). The reduction runs over displacements, not channels, so
 //                             the structure mirrors the forward kernel with the roles swapped: a
 //                             thread owns 4 pixels spaced 2 apart on one row and keeps their
@@ -31,7 +31,7 @@
 //                             through shared memory, and writes 4 x 8 finished gradients per chunk.
 //                             Every value of the other input is read from HBM once per tile
 //                             (halo re-reads hit L2) instead of (2r+1)^2 times.
-//   corr_grad_flip<R>         gB as the same contraction: Gf[n,y,x,k'] = G[n, y+2p'-shift,
+//   corr_grad_flip<R, VEC>    gB as the same contraction: Gf[n,y,x,k'] = G[n, y+2p'-shift,
 //                             x+2o'-shift, D2-1-k'] (shared-memory staged permutation), then
 //                             gB = corr_grad_k1<R, REV=true>(Gf, A): REV walks the displacements
 //                             backwards, which is the reference's summation order for gB, so both
@@ -113,6 +113,22 @@ __device__ __forceinline__ int smem_off(int pixel, int half) {
   return pixel * kCC + ((half ^ ((pixel >> 2) & 1)) << 2);
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// LDGSTS with zero fill: `bytes` = BYTES copies, 0 writes zeros (src is not dereferenced)
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void *src, bool valid) {
+  const int bytes = valid ? BYTES : 0;
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst), "l"(src), "n"(BYTES), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int R>
 struct GradCfg {
   static constexpr int WN = 2 * R + 1, D2 = WN * WN, HALO = 2 * R;
@@ -121,29 +137,35 @@ struct GradCfg {
   static constexpr int BH = kTH + 2 * HALO;
   static constexpr int G_PITCH = kTW * D2 + ((2 - kTW * D2 % 32) + 32) % 32;  // 2 (mod 32) floats
   static constexpr int G_FLOATS = kTH * G_PITCH;
-  static constexpr int B_FLOATS = BH * BPITCH * kCC;
-  static constexpr size_t SMEM = static_cast<size_t>(G_FLOATS + B_FLOATS) * sizeof(float);
+  static constexpr int B_FLOATS = BH * BPITCH * kCC;          // one stage
+  // the coefficient tile is only needed until it sits in registers: it aliases the two stages
+  static constexpr int FLOATS = 2 * B_FLOATS > G_FLOATS ? 2 * B_FLOATS : G_FLOATS;
+  static constexpr size_t SMEM = static_cast<size_t>(FLOATS) * sizeof(float);
 };
 
 // coef [batch, ch, cw, D2]: ch x cw is the extent of the coefficient map; input pixel (y, x) uses
 // coef[y - cshift, x - cshift] (zero outside). other/dst [batch, H, W, C].
 //   dst[n,y,x,c] = 1/C * sum_{p,o} coef[n, y-cshift, x-cshift, k] * other[n, y+2p, x+2o, c]
 // REV: walk k = D2-1 .. 0 instead of 0 .. D2-1.
-template <int R, bool REV>
+// All staging is LDGSTS (cp.async with zero fill = the reference's padding): the copies of a phase
+// are in flight together, and chunk c+1 of the other input lands while chunk c is consumed.
+// GB = bytes per coefficient copy (8 when every tile row starts 8-byte aligned, else 4).
+template <int R, bool REV, int GB>
 __global__ void __launch_bounds__(kThreads, 2)
 corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, int batch, int H, int W,
              int C, int ch, int cw, int cshift, int tiles_x, int tiles_y, float *__restrict__ dst) {
   using Cfg = GradCfg<R>;
   constexpr int WN = Cfg::WN, D2 = Cfg::D2, NB = kPX + 2 * R;
+  constexpr int GE = GB / 4;            // floats per coefficient copy
   extern __shared__ __align__(16) float smem[];
-  float *sg = smem;                     // [kTH][G_PITCH]
-  float *sb = smem + Cfg::G_FLOATS;     // [BH][BPITCH][kCC]
+  float *sg = smem;                     // [kTH][G_PITCH], dead once gk[] is loaded
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // lane bits: [0] parity, [1..2] row & 3, [3..4] group & 3; warps tile 2 (rows) x 2 (x halves)
   const int row = (warp >> 1) * 4 + ((lane >> 1) & 3);
   const int x0 = ((warp & 1) * 4 + (lane >> 3)) * (2 * kPX) + (lane & 1);
   const float sumelems = static_cast<float>(C);
   const int n_tiles = tiles_x * tiles_y * batch;
+  const int n_chunks = C / kCC;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int tx0 = (tile % tiles_x) * kTW;
@@ -153,36 +175,52 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, in
     const float *on = other + static_cast<size_t>(n) * H * W * C;
     float *dn = dst + static_cast<size_t>(n) * H * W * C;
 
-    __syncthreads();   // previous tile finished with sg / sb
-    // ---- coefficients of the tile: rows are contiguous runs of kTW * D2 floats
-    for (int e = threadIdx.x; e < kTH * kTW * D2; e += kThreads) {
-      const int r_ = e / (kTW * D2), f = e % (kTW * D2);
+    __syncthreads();   // the previous tile's last chunk has been consumed
+    // ---- coefficients of the tile: each row is a contiguous run of kTW * D2 floats
+#pragma unroll 4
+    for (int e = threadIdx.x; e < kTH * kTW * D2 / GE; e += kThreads) {
+      const int r_ = e / (kTW * D2 / GE), f = (e % (kTW * D2 / GE)) * GE;
       const int gy = ty0 + r_ - cshift, gx = tx0 + f / D2 - cshift;
-      float v = 0.0f;
-      if (gy >= 0 && gy < ch && gx >= 0 && gx < cw)
-        v = __ldg(cn + (static_cast<size_t>(gy) * cw + gx) * D2 + f % D2);
-      sg[r_ * Cfg::G_PITCH + f] = v;
+      const bool ok = gy >= 0 && gy < ch && gx >= 0 && gx < cw;
+      const float *src = ok ? cn + (static_cast<size_t>(gy) * cw + gx) * D2 + f % D2 : cn;
+      cp_async<GB>(smem_u32(sg + r_ * Cfg::G_PITCH + f), src, ok);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     float gk[kPX][D2];
 #pragma unroll
     for (int j = 0; j < kPX; ++j)
 #pragma unroll
       for (int k = 0; k < D2; ++k) gk[j][k] = sg[row * Cfg::G_PITCH + (x0 + 2 * j) * D2 + k];
+    __syncthreads();   // sg is dead: the stages may be filled
 
-    for (int c0 = 0; c0 < C; c0 += kCC) {
-      __syncthreads();
-      // ---- stage the other input's tile with its halo (zero outside the image = padding)
+    // stage the other input's tile with its halo (zero outside the image = padding)
+    auto issue = [&](int chunk) {
+      float *sb = smem + (chunk & 1) * Cfg::B_FLOATS;
+      const int c0 = chunk * kCC;
+#pragma unroll 6
       for (int e = threadIdx.x; e < Cfg::BH * Cfg::BW * 2; e += kThreads) {
         const int half = e & 1, p = e >> 1;
         const int py = p / Cfg::BW, px = p % Cfg::BW;
         const int gy = ty0 + py - Cfg::HALO, gx = tx0 + px - Cfg::HALO;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-          v = __ldg(reinterpret_cast<const float4 *>(on + (static_cast<size_t>(gy) * W + gx) * C + c0) + half);
-        *reinterpret_cast<float4 *>(sb + smem_off(py * Cfg::BPITCH + px, half)) = v;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        const float *src = ok ? on + (static_cast<size_t>(gy) * W + gx) * C + c0 + 4 * half : on;
+        cp_async<16>(smem_u32(sb + smem_off(py * Cfg::BPITCH + px, half)), src, ok);
+      }
+      cp_async_commit();
+    };
+    issue(0);
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      if (chunk + 1 < n_chunks) {
+        issue(chunk + 1);       // its stage was released by the barrier that ended chunk - 1
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
       __syncthreads();
+      const float *sb = smem + (chunk & 1) * Cfg::B_FLOATS;
+      const int c0 = chunk * kCC;
 
       float4 acc[kPX][2];
 #pragma unroll
@@ -230,6 +268,7 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, in
           }
         }
       }
+      __syncthreads();   // stage (chunk & 1) may be refilled by issue(chunk + 2)
     }
   }
 }
@@ -239,34 +278,48 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, in
 // A CTA produces an FT_H x FT_W tile: the source tile with its halo is read in contiguous rows
 // into shared memory, the permuted tile is written in contiguous rows.
 constexpr int kFH = 8, kFW = 32, kFlipThreads = 256;
-template <int R>
+// VEC: 16-byte copies in and 16-byte stores out; needs out_w, W, HALO + shift all multiples of 4
+// and 16-byte aligned pointers (then no 16-byte granule straddles the edge of either map).
+template <int R, bool VEC>
 __global__ void __launch_bounds__(kFlipThreads)
 corr_grad_flip(const float *__restrict__ grad, int out_h, int out_w, int H, int W, int shift,
                float *__restrict__ gf) {
   constexpr int WN = 2 * R + 1, D2 = WN * WN, HALO = 2 * R;
   constexpr int SW = kFW + 2 * HALO, SH = kFH + 2 * HALO;
-  constexpr int PITCH = SW * D2 + 1;
+  constexpr int PITCH = SW * D2 + 4;            // rows stay 16-byte aligned
+  constexpr int GE = VEC ? 4 : 1;
   extern __shared__ __align__(16) float smem[];
   const int n = blockIdx.z, ty0 = blockIdx.y * kFH, tx0 = blockIdx.x * kFW;
   const float *gn = grad + static_cast<size_t>(n) * out_h * out_w * D2;
   float *fn = gf + static_cast<size_t>(n) * H * W * D2;
-  for (int e = threadIdx.x; e < SH * SW * D2; e += kFlipThreads) {
-    const int r_ = e / (SW * D2), f = e % (SW * D2);
-    const int gy = ty0 + r_ - HALO - shift, gx = tx0 + f / D2 - HALO - shift;
-    float v = 0.0f;
-    if (gy >= 0 && gy < out_h && gx >= 0 && gx < out_w)
-      v = __ldg(gn + (static_cast<size_t>(gy) * out_w + gx) * D2 + f % D2);
-    smem[r_ * PITCH + f] = v;
+  const int gx0 = tx0 - HALO - shift;
+#pragma unroll 4
+  for (int e = threadIdx.x; e < SH * SW * D2 / GE; e += kFlipThreads) {
+    const int r_ = e / (SW * D2 / GE), f = (e % (SW * D2 / GE)) * GE;
+    const int gy = ty0 + r_ - HALO - shift, gx = gx0 + f / D2;
+    const bool ok = gy >= 0 && gy < out_h && gx >= 0 && gx < out_w;
+    const float *src = ok ? gn + (static_cast<long long>(gy) * out_w + gx0) * D2 + f : gn;
+    cp_async<4 * GE>(smem_u32(smem + r_ * PITCH + f), src, ok);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
-  for (int e = threadIdx.x; e < kFH * kFW * D2; e += kFlipThreads) {
-    const int r_ = e / (kFW * D2), f = e % (kFW * D2);
+  auto pick = [&](int r_, int f) {
     const int px = f / D2, k = f % D2;
-    const int y = ty0 + r_, x = tx0 + px;
-    if (y >= H || x >= W) continue;
     const int p = k / WN, o = k % WN;   // p' + R, o' + R
-    fn[(static_cast<size_t>(y) * W + x) * D2 + k] =
-        smem[(r_ + 2 * p) * PITCH + (px + 2 * o) * D2 + (D2 - 1 - k)];
+    return smem[(r_ + 2 * p) * PITCH + (px + 2 * o) * D2 + (D2 - 1 - k)];
+  };
+  for (int e = threadIdx.x; e < kFH * kFW * D2 / GE; e += kFlipThreads) {
+    const int r_ = e / (kFW * D2 / GE), f = (e % (kFW * D2 / GE)) * GE;
+    const int y = ty0 + r_, x = tx0 + f / D2;
+    if (y >= H || x >= W) continue;
+    float *d = fn + (static_cast<long long>(y) * W + tx0) * D2 + f;
+    if constexpr (VEC) {
+      // W % 4 == 0 and tx0 % 4 == 0: the four floats lie in columns < W together
+      *reinterpret_cast<float4 *>(d) = make_float4(pick(r_, f), pick(r_, f + 1), pick(r_, f + 2), pick(r_, f + 3));
+    } else {
+      *d = pick(r_, f);
+    }
   }
 }
 
@@ -279,26 +332,39 @@ int launch_k1(const float *grad, const float *a, const float *b, const GradGeom 
   const long long n_tiles = static_cast<long long>(tiles_x) * tiles_y * g.batch;
   if (n_tiles > 0x7FFFFFFFll) return 1;
   const int grid = static_cast<int>(n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs);
-  DODT_CUDA_TRY(cudaFuncSetAttribute(corr_grad_k1<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(Cfg::SMEM)));
-  DODT_CUDA_TRY(cudaFuncSetAttribute(corr_grad_k1<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(Cfg::SMEM)));
-  if (ga) {
-    corr_grad_k1<R, false><<<grid, kThreads, Cfg::SMEM, stream>>>(
-        grad, b, g.batch, g.H, g.W, g.C, g.out_h, g.out_w, shift, tiles_x, tiles_y, ga);
+  auto run = [&](auto kernel, const float *coef, const float *other, int ch, int cw, int cshift,
+                 float *dst) -> int {
+    DODT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(Cfg::SMEM)));
+    kernel<<<grid, kThreads, Cfg::SMEM, stream>>>(coef, other, g.batch, g.H, g.W, g.C, ch, cw, cshift,
+                                                  tiles_x, tiles_y, dst);
     DODT_AFTER_LAUNCH();
+    return DODT_OK;
+  };
+  // 8-byte coefficient copies need every tile row to start 8-byte aligned (kTW is even)
+  auto wide = [](const float *p, int cw, int cshift) {
+    return reinterpret_cast<uintptr_t>(p) % 8 == 0 && cw % 2 == 0 && cshift % 2 == 0;
+  };
+  if (ga) {
+    const int rc = wide(grad, g.out_w, shift)
+                       ? run(corr_grad_k1<R, false, 8>, grad, b, g.out_h, g.out_w, shift, ga)
+                       : run(corr_grad_k1<R, false, 4>, grad, b, g.out_h, g.out_w, shift, ga);
+    if (rc != DODT_OK) return rc;
   }
   if (gb) {
     constexpr int D2 = Cfg::D2, HALO = Cfg::HALO;
-    const size_t fsmem = (static_cast<size_t>(kFH + 2 * HALO) * ((kFW + 2 * HALO) * D2 + 1)) * sizeof(float);
-    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_grad_flip<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t fsmem = (static_cast<size_t>(kFH + 2 * HALO) * ((kFW + 2 * HALO) * D2 + 4)) * sizeof(float);
+    const bool vec = g.out_w % 4 == 0 && g.W % 4 == 0 && (HALO + shift) % 4 == 0 &&
+                     reinterpret_cast<uintptr_t>(grad) % 16 == 0;   // ws is 16-byte aligned
+    auto flip = vec ? corr_grad_flip<R, true> : corr_grad_flip<R, false>;
+    DODT_CUDA_TRY(cudaFuncSetAttribute(flip, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(fsmem)));
     dim3 fgrid(ceil_div(g.W, kFW), ceil_div(g.H, kFH), g.batch);
-    corr_grad_flip<R><<<fgrid, kFlipThreads, fsmem, stream>>>(grad, g.out_h, g.out_w, g.H, g.W, shift, ws);
+    flip<<<fgrid, kFlipThreads, fsmem, stream>>>(grad, g.out_h, g.out_w, g.H, g.W, shift, ws);
     DODT_AFTER_LAUNCH();
-    corr_grad_k1<R, true><<<grid, kThreads, Cfg::SMEM, stream>>>(
-        ws, a, g.batch, g.H, g.W, g.C, g.H, g.W, 0, tiles_x, tiles_y, gb);
-    DODT_AFTER_LAUNCH();
+    const int rc = wide(ws, g.W, 0) ? run(corr_grad_k1<R, true, 8>, ws, a, g.H, g.W, 0, gb)
+                                    : run(corr_grad_k1<R, true, 4>, ws, a, g.H, g.W, 0, gb);
+    if (rc != DODT_OK) return rc;
   }
   return DODT_OK;
 }

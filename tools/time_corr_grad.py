@@ -34,3 +34,15 @@ for name, na, nb, nbytes in (("both", True, True, G + 4 * IN), ("grad_a", True, 
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     print("%-7s %.1f us  %.0f GB/s algorithmic (%.1f MB)" % (name, us, nbytes / us / 1e3, nbytes / 1e6))
+
+# per-kernel durations (CUPTI through torch.profiler)
+try:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(6):
+            run(bufs[i % 3], True, True)
+        torch.cuda.synchronize()
+    for ev in prof.key_averages():
+        print("  %-60s n=%d  avg %.1f us" % (ev.key[:60], ev.count, ev.device_time_total / max(ev.count, 1)))
+except Exception as exc:   # noqa: BLE001
+    print("profiler unavailable:", exc)
