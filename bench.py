@@ -8,10 +8,11 @@ correlation + NMS) on N B200s, with the HBM roofline of the dominant kernel and 
 A "step" is one frame of BASELINE.json configs[1] (KITTI car config: 120k-point cloud -> 6 BEV maps
 and occupancy, 89 600-anchor filter, 3x3 RPN crops, NMS 0.8/1024, tau=1 BEV-feature correlation,
 7x7 crops of BEV/image/correlation maps for 1024 proposals, NMS 0.01/100) on synthetic
-KITTI-shaped data. `value` is timed with every input resident in HBM (CUDA-graph replay per frame,
-three resident frame slots cycled so that each step reads > 200 MB of inputs the previous step did
-not touch); `e2e` re-times the same steps through the public Python API with all inputs in pinned
-host memory, H2D and D2H inside the timed region.
+KITTI-shaped data. `value` is timed with every input resident in HBM: CUDA graphs of --group
+consecutive frames (their correlations are one frame-stream launch) replayed round-robin over
+--slots resident frame slots on one stream per group, so that each step reads inputs the previous
+steps did not touch (12 slots x 135 MB > the 126 MB L2); `e2e` re-times the same steps through the
+public Python API with all inputs in pinned host memory, H2D and D2H inside the timed region.
 """
 import argparse
 import json
@@ -37,6 +38,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots", type=int, default=12)
+    ap.add_argument("--group", type=int, default=4,
+                    help="consecutive frames per CUDA graph: their correlations share one launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -206,7 +209,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     fe = FrontEnd()
+    G = max(1, args.group)
     n_slots = max(2, args.slots)
+    n_slots = (n_slots + G - 1) // G * G       # whole groups
+    n_groups = n_slots // G
     slots = [fe.new_slot() for _ in range(n_slots)]
     # one KITTI-tracking-shaped stream per GPU: rank r reads frames of "sequence" r
     hosts = [HostFrame(fe).fill(synth.frame_inputs(CONFIG_ID, 1000 * rank + i), sequence=rank, frame=i)
@@ -217,10 +223,20 @@ def run_ours(args):
     for s_, h in zip(slots, hosts):
         h.upload(s_)
     torch.cuda.synchronize()
+    # One graph per GROUP of G consecutive frames: the G correlations are one frame-stream launch
+    # (the feature map two neighbouring pairs share is read from HBM once), the G per-frame chains
+    # run on branch streams. Single-frame graphs serve the K mod G frames that end a run.
     graphs, launches = [], 0
-    for i in range(n_slots):
-        g, launches = fe.capture(slots[i], slots[i - 1], block)
-        graphs.append(g)
+    for g_ in range(n_groups):
+        gr, launches = fe.capture_group(slots[g_ * G:(g_ + 1) * G], slots[g_ * G - 1], block)
+        graphs.append(gr)
+    singles = {}
+    launches_single = launches // G
+
+    def single(i):
+        if i not in singles:
+            singles[i], _ = fe.capture(slots[i], slots[i - 1], block)
+        return singles[i]
     torch.cuda.synchronize()
 
     def barrier():
@@ -233,15 +249,22 @@ def run_ours(args):
     # each resident slot replays its graph on its own CUDA stream: the latency-bound stages of one
     # frame (NMS, scans, compaction) overlap the bandwidth-bound stages of its neighbours.
     K, Wm = args.steps, max(args.warmup, 3)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(n_slots)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_groups)]
     main = torch.cuda.current_stream()
+    for i in range(K % G):      # the tail graphs are captured before anything is timed
+        single(((K // G) % n_groups) * G + i)
 
     def replay_round_robin(n):
+        """exactly n frames: n // G group replays, then n % G single frames of the next group"""
         for st in streams:
             st.wait_stream(main)
-        for i in range(n):
-            with torch.cuda.stream(streams[i % n_slots]):
-                graphs[i % n_slots].replay()
+        q, r = divmod(n, G)
+        for i in range(q):
+            with torch.cuda.stream(streams[i % n_groups]):
+                graphs[i % n_groups].replay()
+        with torch.cuda.stream(streams[q % n_groups]):
+            for i in range(r):
+                single((q % n_groups) * G + i).replay()
         for st in streams:
             main.wait_stream(st)
 
@@ -281,11 +304,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     la.record()
-    for i in range(min(K, 60)):
-        graphs[i % n_slots].replay()
+    for i in range(15):
+        graphs[i % n_groups].replay()
     lb.record()
     torch.cuda.synchronize()
-    frame_latency_us = la.elapsed_time(lb) * 1e3 / min(K, 60)
+    group_latency_us = la.elapsed_time(lb) * 1e3 / 15
 
     # ------------------------------------------------------------------ per-stage + dominant kernel
     c = fe.cfg
@@ -330,9 +353,6 @@ def run_ours(args):
                                                                c.rpn_crop, 0.0, n_dev=s.n_kept),
         "S5_rpn_nms": lambda s, p: ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx,
                                            n_keep=s.n_top, workspace=s.ws_nms_rpn, n_dev=s.n_kept, max_windows=c.nms_max_windows),
-        "S4_correlation": lambda s, p: ops.correlation(p.bev_feat, s.bev_feat, 1, c.corr_max_displacement, 1,
-                                                       c.corr_stride_2, c.corr_padding, out=s.corr,
-                                                       max_ctas=c.corr_max_ctas),
         "S3_avod_crops": lambda s, p: ops.crop_and_resize_multi([(s.bev_feat, s.prop_bev_boxes, s.bev_rois),
                                                                  (s.img_feat, s.prop_img_boxes, s.img_rois),
                                                                  (s.corr, s.prop_bev_boxes, s.corr_rois)],
@@ -341,25 +361,62 @@ def run_ours(args):
                                              n_keep=s.n_final, workspace=s.ws_nms_final, n_dev=s.n_top),
     }
     stage_us = {k: time_stage(f) for k, f in stage_fns.items()}
-    # the same kernel when it has the GPU to itself (two CTAs per SM instead of the runner's one)
-    corr_alone_us = time_stage(lambda s, p: ops.correlation(p.bev_feat, s.bev_feat, 1, c.corr_max_displacement,
-                                                            1, c.corr_stride_2, c.corr_padding, out=s.corr))
+
+    def time_corr_launch(max_ctas):
+        """Mean device time of ONE correlation launch as the frame runner issues it: the G pairs of
+        a group of consecutive frames (dodt_correlation_stream), graph-captured per group."""
+        def launch(g_):
+            grp = slots[g_ * G:(g_ + 1) * G]
+            if G == 1:
+                ops.correlation(slots[g_ - 1].bev_feat, grp[0].bev_feat, 1, c.corr_max_displacement, 1,
+                                c.corr_stride_2, c.corr_padding, out=grp[0].corr, max_ctas=max_ctas)
+            else:
+                ops.correlation_stream([slots[g_ * G - 1].bev_feat] + [x.bev_feat for x in grp], 1,
+                                       c.corr_max_displacement, 1, c.corr_stride_2, c.corr_padding,
+                                       outs=[x.corr for x in grp], max_ctas=max_ctas)
+        cg = []
+        for g_ in range(n_groups):
+            launch(g_)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                launch(g_)
+            cg.append(gr)
+        for gr in cg:
+            gr.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_rep = max(6, reps // G)
+        a.record()
+        for i in range(n_rep):
+            cg[i % n_groups].replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / n_rep   # us per launch
+
+    corr_launch_us = time_corr_launch(c.corr_max_ctas)
+    # the same launch when it has the GPU to itself (two CTAs per SM instead of the runner's one)
+    corr_alone_us = time_corr_launch(0)
+    stage_us["S4_correlation"] = corr_launch_us / G     # per frame, like the other stages
     n_kept = int(slots[0].n_kept.item())
     n_top = int(slots[0].n_top[0].item())
     abytes = fe.algorithmic_bytes(n_points, n_kept, n_top)
     peak, peak_src = measured_peak()
-    corr_us = stage_us["S4_correlation"]            # one launch of corr_tile_k1 per call
-    achieved = abytes["S4"] / (corr_us * 1e-6) / 1e9
+    launch_bytes = G * abytes["S4"]                 # SURVEY 8(d): 199.36 MB per pair x G pairs per launch
+    achieved = launch_bytes / (corr_launch_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": "corr_async_k1<2,4,0,8,2> (S4 correlation, %.0f%% of the step's "
                                           "algorithmic bytes)" % (100.0 * abytes["S4"] / abytes["total"]),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": abytes["S4"],
-                "launch": "as the frame runner launches it: %d persistent CTAs (one per SM), the rest "
-                          "of each SM left to the other stages of neighbouring frames" % c.corr_max_ctas,
-                "standalone": {"us": corr_alone_us, "achieved": abytes["S4"] / (corr_alone_us * 1e-6) / 1e9,
-                               "frac": abytes["S4"] / (corr_alone_us * 1e-6) / 1e9 / peak,
-                               "launch": "296 CTAs (two per SM), nothing else running"},
+                "algorithmic_bytes_per_launch": launch_bytes, "pairs_per_launch": G,
+                "launch_us": corr_launch_us,
+                "launch": "as the frame runner launches it: the %d frame pairs of a group in one "
+                          "frame-stream launch (a map shared by two pairs is read from HBM once), %d "
+                          "persistent CTAs (one per SM), the rest of each SM left to the other stages "
+                          "of neighbouring frames" % (G, c.corr_max_ctas),
+                "standalone": {"us": corr_alone_us, "achieved": launch_bytes / (corr_alone_us * 1e-6) / 1e9,
+                               "frac": launch_bytes / (corr_alone_us * 1e-6) / 1e9 / peak,
+                               "launch": "the same launch with 296 CTAs (two per SM), nothing else running"},
                 "frame": {"algorithmic_bytes": abytes["total"],
                           "achieved": abytes["total"] * fps / world / 1e9,
                           "frac": abytes["total"] * fps / world / 1e9 / peak},
@@ -367,36 +424,40 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ e2e: host buffers
     # Every step: H2D of the frame's inputs from pinned host memory (one packed sensor buffer +
-    # the four feature maps), the frame graph, D2H of the packed results — all on the slot's own
-    # stream, so the copies of one frame overlap the kernels of its neighbours.
+    # the four feature maps), the frame's share of its group graph, D2H of the packed results — all
+    # on the group's own stream, so the copies of one group overlap the kernels of its neighbours.
     e2e = None
     if not args.no_e2e:
         h2d = hosts[0].h2d_bytes
         d2h = hosts[0].result_buf.numel()
-        done_ev = [None] * n_slots      # graph of slot j finished (it read slots j and j-1)
-        up_ev = [None] * n_slots        # inputs of slot j are on the device
+        done_ev = [None] * n_groups     # graph of group g finished (it read its slots and the last slot of group g-1)
+        up_ev = [None] * n_groups       # inputs of group g are on the device
 
         def e2e_loop(n, features):
+            """n frames (a multiple of G): per group, H2D of its G frames, the group graph, D2H."""
             for st in streams:
                 st.wait_stream(main)
-            for i in range(n):
-                j = i % n_slots
-                st = streams[j]
+            for i in range(n // G):
+                g_ = i % n_groups
+                st = streams[g_]
+                grp = range(g_ * G, (g_ + 1) * G)
                 with torch.cuda.stream(st):
-                    # slot j's inputs were last read by the graph of slot j+1 (as its previous frame)
-                    ev = done_ev[(j + 1) % n_slots]
+                    # the last slot of this group was read by the graph of group g+1 (its previous frame)
+                    ev = done_ev[(g_ + 1) % n_groups]
                     if ev is not None:
                         st.wait_event(ev)
-                    hosts[j].upload(slots[j], features)
-                    up_ev[j] = torch.cuda.Event()
-                    up_ev[j].record(st)
-                    ev = up_ev[(j - 1) % n_slots]   # this graph reads slot j-1's BEV features
+                    for j in grp:
+                        hosts[j].upload(slots[j], features)
+                    up_ev[g_] = torch.cuda.Event()
+                    up_ev[g_].record(st)
+                    ev = up_ev[(g_ - 1) % n_groups]   # this graph reads the last BEV map of group g-1
                     if ev is not None:
                         st.wait_event(ev)
-                    graphs[j].replay()
-                    done_ev[j] = torch.cuda.Event()
-                    done_ev[j].record(st)
-                    hosts[j].download(slots[j])
+                    graphs[g_].replay()
+                    done_ev[g_] = torch.cuda.Event()
+                    done_ev[g_].record(st)
+                    for j in grp:
+                        hosts[j].download(slots[j])
             for st in streams:
                 main.wait_stream(st)
 
@@ -413,7 +474,7 @@ def run_ours(args):
                 dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
             return float(t_ms.item())
 
-        Ke = max(6, min(K, 60))
+        Ke = max(2 * G, min(K, 60) // G * G)
         ems = timed_e2e(Ke, True)
         e2e = {"value": Ke * world / (ems / 1e3), "unit": "frames/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
@@ -422,7 +483,7 @@ def run_ours(args):
                        "pinned host memory each step; detection lists copied back; PCIe-bound"}
         # the same with the network feature maps left on the device (where the reference has them:
         # they are TF GPU tensors); only sensor data and head outputs cross PCIe
-        Ks = max(6, min(K, 600))
+        Ks = max(2 * G, min(K, 600) // G * G)
         sms = timed_e2e(Ks, False)
         e2e["sensor_only"] = {
             "value": Ks * world / (sms / 1e3), "unit": "frames/s", "steps": Ks,
@@ -452,11 +513,14 @@ def run_ours(args):
                        "anchors_kept": n_kept, "proposals": n_top,
                        "l2": "inputs %.0f MB/step cycled over %d resident frame slots (> 126 MB L2)"
                              % (hosts[0].h2d_bytes / 1e6, n_slots),
+                       "frames_per_graph": G,
                        "parallelism": "one frame stream per GPU, no data-path collective; one "
                                       "all_gather of detection lists per shard"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches * K, "launches_per_step": launches, "clocks": clocks,
-            "frame_latency_us_single_stream": frame_latency_us, "streams": n_slots,
+            "gpu_launches": launches * (K // G) + launches_single * (K % G),
+            "launches_per_step": launches / G, "clocks": clocks,
+            "group_latency_us_single_stream": group_latency_us, "frames_per_graph": G,
+            "streams": n_groups,
             "gathered": {"ranks": len(gathered), "frames_per_rank": int(block.rows.shape[0]),
                          "bytes_per_rank": int(block.rows.numel() * 4 + block.counts.numel() * 4
                                                + block.frame_ids.numel() * 4),

@@ -15,6 +15,7 @@ MAX_SLICES = 15
 MAX_DENSITY_LUT = 64
 NMS_WINDOW = 1536
 NMS_CHUNK_WINDOWS = 2
+CORR_STREAM_MAX_PAIRS = 8
 BEV_STATS_LEN = 24
 STAT_DENSITY, STAT_OCC, STAT_TOUCHED, STAT_OVERFLOW, STAT_OOB = 16, 17, 18, 19, 20
 
@@ -101,6 +102,9 @@ SIGNATURES = {
                                  c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "dodt_correlation_shared": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                         c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
+                                        c_void_p]),
+    "dodt_correlation_stream": (c_int, [POINTER(c_void_p), c_int32, POINTER(c_void_p), c_int32, c_int32,
+                                        c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                         c_void_p]),
     "dodt_correlation_grad_workspace_bytes": (c_size_t, [c_int32] * 9),
     "dodt_correlation_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,

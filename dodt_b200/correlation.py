@@ -49,6 +49,20 @@ def correlation(input_a, input_b, kernel_size=1, max_displacement=20, stride_1=1
     return out.cpu().numpy() if was_numpy else out
 
 
+def correlation_stream(feature_maps, kernel_size=1, max_displacement=20, stride_1=1, stride_2=2,
+                       padding=20):
+    """`correlation` over the consecutive key frames of a sequence: returns
+    [correlation(f[0], f[1]), correlation(f[1], f[2]), ...], each bit-identical to the pairwise call.
+    The reference runs the op once per sample pair (dt_rpn_model.py:324-331 inside the inference
+    loop) and therefore reads every BEV feature map twice; here neighbouring pairs share a launch
+    and the common map comes from HBM once. feature_maps: sequence of [1, H, W, C] arrays/tensors."""
+    was_numpy = not torch.is_tensor(feature_maps[0])
+    maps = [_as_cuda(m) for m in feature_maps]
+    outs = ops.correlation_stream(maps, int(kernel_size), int(max_displacement), int(stride_1),
+                                  int(stride_2), int(padding))
+    return [o.cpu().numpy() for o in outs] if was_numpy else outs
+
+
 def correlation_grad(gradients, input_a, input_b, kernel_size=1, max_displacement=20, stride_1=1,
                      stride_2=2, pad=20):
     """The CorrelationGrad op (argument order of correlation.py:37-44): returns

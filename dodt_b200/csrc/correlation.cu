@@ -32,6 +32,10 @@ namespace dodt {
 int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, int r, int out_h,
                     int out_w, int shift, float *out, int max_ctas, cudaStream_t stream);
 
+int correlation_stream_tma(const float *const *maps, int n_pairs, float *const *outs, int H, int W,
+                           int C, int r, int out_h, int out_w, int shift, int max_ctas,
+                           cudaStream_t stream);
+
 namespace {
 
 struct CorrGeom {
@@ -315,6 +319,40 @@ int dodt_correlation_shared(const float *a, const float *b, int32_t batch, int32
   else
     corr_generic<1><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a, b, g, total, out);
   DODT_AFTER_LAUNCH();
+  return DODT_OK;
+}
+
+int dodt_correlation_stream(const float *const *maps, int32_t n_maps, float *const *outs,
+                            int32_t height, int32_t width, int32_t channels, int32_t kernel_size,
+                            int32_t max_displacement, int32_t stride_1, int32_t stride_2,
+                            int32_t pad, int32_t max_ctas, dodt_stream_t stream_) {
+  using namespace dodt;
+  if (!maps || !outs || n_maps < 2 || max_ctas < 0) return DODT_EINVAL;
+  for (int k = 0; k < n_maps; ++k)
+    if (!maps[k] || (k + 1 < n_maps && !outs[k])) return DODT_EINVAL;
+  CorrGeom g;
+  const int rc = fill_geom(1, height, width, channels, kernel_size, max_displacement, stride_1,
+                           stride_2, pad, &g);
+  if (rc != DODT_OK) return rc;
+  cudaStream_t stream = as_stream(stream_);
+  int j = 0;
+  if (g.ks == 1 && g.s1 == 1 && g.s2 == 2) {
+    // groups of up to DODT_CORR_STREAM_MAX_PAIRS pairs per launch; neighbouring groups share a map
+    while (j < n_maps - 1) {
+      const int n = n_maps - 1 - j < DODT_CORR_STREAM_MAX_PAIRS ? n_maps - 1 - j : DODT_CORR_STREAM_MAX_PAIRS;
+      const int done = correlation_stream_tma(maps + j, n, outs + j, g.H, g.W, g.C, g.r, g.out_h,
+                                              g.out_w, g.md - g.pad, max_ctas, stream);
+      if (done < 0) return done;
+      if (done > 0) break;   // not applicable: pair by pair below
+      j += n;
+    }
+  }
+  for (; j < n_maps - 1; ++j) {
+    const int rc2 = dodt_correlation_shared(maps[j], maps[j + 1], 1, height, width, channels, kernel_size,
+                                            max_displacement, stride_1, stride_2, pad, outs[j], max_ctas,
+                                            stream_);
+    if (rc2 != DODT_OK) return rc2;
+  }
   return DODT_OK;
 }
 

@@ -251,11 +251,17 @@ corr_tma_k1(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 // from one shared-memory and one global base, so the issue cost is ~150 instructions per 900 of
 // math, and one __syncthreads per unit both publishes stage u and frees stage u-1.
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxStreamPairs = DODT_CORR_STREAM_MAX_PAIRS;
 struct CorrAsyncGeom {
   int batch, H, W, C, out_h, out_w, shift;
   int tiles_x, tiles_y, n_tiles;
   int pow2;       // C is a power of two: divide by multiplying with the exact reciprocal
   float inv_c;
+  // frame-stream mode (n_stream > 0): item n correlates maps[n] with maps[n + 1] into outs[n];
+  // the a / b / out kernel arguments are unused
+  int n_stream;
+  const float *maps[kMaxStreamPairs + 1];
+  float *outs[kMaxStreamPairs];
 };
 
 // PX pixels per thread (spaced 2 apart). PX = 4: 256 threads, 100 accumulators, 10 FMAs per
@@ -303,11 +309,15 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
   auto prepare = [&](int u) {
     const int tile = blockIdx.x + (u / n_chunks) * gridDim.x;
     const int c0 = (u % n_chunks) * kCC + lhalf * 4;
-    const int tx = tile % g.tiles_x;
-    const int ty = (tile / g.tiles_x) % g.tiles_y;
-    const int n = tile / (g.tiles_x * g.tiles_y);
+    // batch-interleaved tile order: the same spatial tile of consecutive batch items is worked on
+    // at the same time (by neighbouring CTAs), so a map that two items share is fetched once
+    const int n = tile % g.batch, sp = tile / g.batch;
+    const int tx = sp % g.tiles_x;
+    const int ty = sp / g.tiles_x;
     const uint32_t sbase = smem_base + static_cast<uint32_t>(u % NST) * Cfg::STAGE1_OFF;
     const size_t img = static_cast<size_t>(n) * g.H * g.W * g.C;
+    const float *a_img = g.n_stream ? g.maps[n] : a + img;
+    const float *b_img = g.n_stream ? g.maps[n + 1] : b + img;
 #pragma unroll
     for (int rr = 0; rr < kRowsPerThread; ++rr) {
       const int lr = ly + rr * kRowThreads;
@@ -317,7 +327,7 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
       const int gy = ty * TH + g.shift - halo + trow;
       const int gx0 = tx * kTW + g.shift - halo + lpx;
       const bool row_ok = static_cast<unsigned>(gy) < static_cast<unsigned>(g.H);
-      l_src[rr] = (is_b ? b : a) + img + (static_cast<long long>(gy) * g.W + gx0) * g.C + c0;
+      l_src[rr] = (is_b ? b_img : a_img) + (static_cast<long long>(gy) * g.W + gx0) * g.C + c0;
       l_dst[rr] = sbase + (is_b ? Cfg::A_BYTES : 0) +
                   static_cast<uint32_t>(swz(trow * (is_b ? Cfg::BW : Cfg::AW) + lpx, lhalf)) * 4u;
       l_gx0[rr] = row_ok ? gx0 : (1 << 30);
@@ -427,9 +437,9 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     }
 
     // ---- epilogue: stage the tile through the just-consumed stage (+ spare), coalesced stores
-    const int tx = tile % g.tiles_x;
-    const int ty = (tile / g.tiles_x) % g.tiles_y;
-    const int n = tile / (g.tiles_x * g.tiles_y);
+    const int n = tile % g.batch, sp = tile / g.batch;
+    const int tx = sp % g.tiles_x;
+    const int ty = sp / g.tiles_x;
     float *stg = reinterpret_cast<float *>(
         smem + (stage == NST - 1 ? stage * Cfg::STAGE1_OFF + Cfg::STAGE_BYTES - Cfg::OUT_BYTES
                                  : stage * Cfg::STAGE1_OFF));
@@ -453,8 +463,9 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     __syncthreads();
     const int valid_rows = min(TH, g.out_h - ty * TH);
     const int valid_floats = min(kTW, g.out_w - tx * kTW) * D2;
-    float *gout = out + ((static_cast<size_t>(n) * g.out_h + ty * TH) * g.out_w + tx * kTW) * D2;
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) % 8 == 0) && ((g.out_w * D2) % 2 == 0) &&
+    float *out_img = g.n_stream ? g.outs[n] : out + static_cast<size_t>(n) * g.out_h * g.out_w * D2;
+    float *gout = out_img + (static_cast<size_t>(ty * TH) * g.out_w + tx * kTW) * D2;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out_img) % 8 == 0) && ((g.out_w * D2) % 2 == 0) &&
                         (valid_floats % 2 == 0);
     for (int r = warp; r < ((DBG & 4) ? 0 : valid_rows); r += kWarps) {
       const float *src = stg + r * Cfg::OUT_PITCH;
@@ -533,7 +544,8 @@ int launch(const float *a, const float *b, int N, int H, int W, int C, int out_h
 
 template <int R, int PX, int FRONT, int TH = kTH, int CTAS = 1, int NST = 2, int DBG = 0>
 int launch_async(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w,
-                 int shift, float *out, int max_ctas, cudaStream_t stream) {
+                 int shift, float *out, int max_ctas, cudaStream_t stream,
+                 const float *const *maps = nullptr, float *const *outs = nullptr) {
   using Cfg = TmaCfg<R, TH>;
   constexpr int kThr = kTW / (2 * PX) * 2 * TH;
   constexpr int smem_bytes = (NST - 1) * Cfg::STAGE1_OFF + Cfg::STAGE_BYTES + 64;
@@ -551,6 +563,14 @@ int launch_async(const float *a, const float *b, int N, int H, int W, int C, int
   g.n_tiles = g.tiles_x * g.tiles_y * N;
   g.pow2 = (C & (C - 1)) == 0 ? 1 : 0;
   g.inv_c = 1.0f / static_cast<float>(C);
+  g.n_stream = 0;
+  for (int k = 0; k <= kMaxStreamPairs; ++k) g.maps[k] = nullptr;
+  for (int k = 0; k < kMaxStreamPairs; ++k) g.outs[k] = nullptr;
+  if (maps) {   // frame-stream mode: N pairs over N + 1 maps
+    g.n_stream = N;
+    for (int k = 0; k <= N; ++k) g.maps[k] = maps[k];
+    for (int k = 0; k < N; ++k) g.outs[k] = outs[k];
+  }
   int grid = g.n_tiles < CTAS * kNumSMs ? g.n_tiles : CTAS * kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;   // persistent CTAs: any count works
   corr_async_k1<R, PX, FRONT, TH, CTAS, NST, DBG><<<grid, kThr, smem_bytes, stream>>>(a, b, g, out);
@@ -621,6 +641,26 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
   switch (r) {
     case 1: return launch_async<1, 4, 0, 8, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
     case 2: return launch_async<2, 4, 0, 8, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+    default: return 1;
+  }
+}
+
+// Frame-stream form: pair j correlates maps[j] (frame t) with maps[j + 1] (frame t + 1) into
+// outs[j], all pairs in ONE launch with batch-interleaved tiles, so that a map shared by two pairs
+// (B of pair j, A of pair j + 1) is read from HBM once and served from L2 the second time.
+// maps / outs: host arrays of device pointers. Returns like correlation_tma.
+int correlation_stream_tma(const float *const *maps, int n_pairs, float *const *outs, int H, int W,
+                           int C, int r, int out_h, int out_w, int shift, int max_ctas,
+                           cudaStream_t stream) {
+  if (n_pairs < 1 || n_pairs > kMaxStreamPairs || C % kCC != 0) return 1;
+  for (int k = 0; k <= n_pairs; ++k)
+    if (reinterpret_cast<uintptr_t>(maps[k]) % 16) return 1;
+  if (static_cast<long long>(out_h) * out_w < 1024) return 1;
+  switch (r) {
+    case 1: return launch_async<1, 4, 0, 8, 2>(nullptr, nullptr, n_pairs, H, W, C, out_h, out_w, shift,
+                                               nullptr, max_ctas, stream, maps, outs);
+    case 2: return launch_async<2, 4, 0, 8, 2>(nullptr, nullptr, n_pairs, H, W, C, out_h, out_w, shift,
+                                               nullptr, max_ctas, stream, maps, outs);
     default: return 1;
   }
 }

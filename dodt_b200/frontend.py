@@ -224,6 +224,7 @@ class FrontEnd:
                                               c.height_lo, c.height_hi, c.num_slices, True,
                                               c.occ_lo, c.occ_hi)
         self.side_stream = torch.cuda.Stream(device=self.device)
+        self.branch_streams = []   # one per extra frame of an enqueue_group
         f32, i32 = torch.float32, torch.int32
         nA = self.num_anchors
         self.sensor_layout, self.sensor_bytes = _layout([
@@ -246,15 +247,48 @@ class FrontEnd:
         detections are appended to it (the list that a sharded run gathers once per shard).
         skip: stage names left out (profiling only: "S1", "S2", "S3a", "S5a", "S4", "S3b", "S5b").
         Capturable into a CUDA graph; returns the number of library kernels launched."""
-        c, s = self.cfg, slot
+        return self.enqueue_group([slot], prev_slot, block, skip)
+
+    def enqueue_group(self, slots, prev_slot, block=None, skip=()):
+        """Enqueue k CONSECUTIVE frames of a stream (slots[0] follows prev_slot, slots[j] follows
+        slots[j-1]). The k correlations go out as ONE frame-stream launch on the side stream
+        (dodt_correlation_stream: the feature map that pair j and pair j+1 share is read from HBM
+        once); the per-frame chains S1..S5a run on a branch stream each and join the correlation
+        before their S3b. Same results as k calls of `enqueue`."""
+        c = self.cfg
+        k = len(slots)
         before = ops.launch_count()
         main = torch.cuda.current_stream()
-        # S4 on the side stream (independent of the point cloud)
+        while len(self.branch_streams) < k - 1:
+            self.branch_streams.append(torch.cuda.Stream(device=self.device))
+        lanes = [main] + self.branch_streams[:k - 1]
+        # fork: S4 on the side stream (independent of the point clouds), frame j on lane j
         self.side_stream.wait_stream(main)
+        for st in lanes[1:]:
+            st.wait_stream(main)
         if "S4" not in skip:
             with torch.cuda.stream(self.side_stream):
-                ops.correlation(prev_slot.bev_feat, s.bev_feat, 1, c.corr_max_displacement, 1,
-                                c.corr_stride_2, c.corr_padding, out=s.corr, max_ctas=c.corr_max_ctas)
+                if k == 1:
+                    ops.correlation(prev_slot.bev_feat, slots[0].bev_feat, 1, c.corr_max_displacement, 1,
+                                    c.corr_stride_2, c.corr_padding, out=slots[0].corr,
+                                    max_ctas=c.corr_max_ctas)
+                else:
+                    ops.correlation_stream([prev_slot.bev_feat] + [s.bev_feat for s in slots], 1,
+                                           c.corr_max_displacement, 1, c.corr_stride_2, c.corr_padding,
+                                           outs=[s.corr for s in slots], max_ctas=c.corr_max_ctas)
+        for s, st in zip(slots, lanes):
+            with torch.cuda.stream(st):
+                self._enqueue_pre(s, skip)
+        for s, st in zip(slots, lanes):
+            with torch.cuda.stream(st):
+                st.wait_stream(self.side_stream)          # S3b: the corr crop needs S4
+                self._enqueue_post(s, block, skip)
+        for st in lanes[1:]:
+            main.wait_stream(st)
+        return ops.launch_count() - before
+
+    def _enqueue_pre(self, s, skip):
+        c = self.cfg
         if "S1" not in skip:
             ops.bev_slices(s.points[:, :s.n_points], self.bev_params, s.maps, s.occ, s.stats, s.ws_bev)
         if "S2" not in skip:
@@ -281,8 +315,9 @@ class FrontEnd:
             # image boxes only for the proposals that survived (eight fp64 corner projections each)
             ops.rpn_decode(self.anchors, s.rpn_offsets, s.kept_idx, s.n_top, self.bev_extents4,
                            c.stereo_calib_p2, c.image_shape, None, s.prop_img_boxes, idx2=s.top_idx)
-        # S3b (the corr crop needs S4)
-        main.wait_stream(self.side_stream)
+
+    def _enqueue_post(self, s, block, skip):
+        c = self.cfg
         if "S3b" not in skip:
             ops.crop_and_resize_multi([(s.bev_feat, s.prop_bev_boxes, s.bev_rois),
                                        (s.img_feat, s.prop_img_boxes, s.img_rois),
@@ -294,16 +329,19 @@ class FrontEnd:
         if block is not None:
             ops.emit_detections(s.prop_bev_boxes, s.final_scores, s.final_idx, s.n_final, block,
                                 frame_id=s.frame_id)
-        return ops.launch_count() - before
 
     def capture(self, slot, prev_slot, block=None, skip=()):
         """Warm up eagerly once (sets kernel attributes), then capture `enqueue` into a graph.
         Returns (graph, kernels per replay)."""
-        self.enqueue(slot, prev_slot, block)
+        return self.capture_group([slot], prev_slot, block, skip)
+
+    def capture_group(self, slots, prev_slot, block=None, skip=()):
+        """`enqueue_group` as one CUDA graph. Returns (graph, kernels per replay)."""
+        self.enqueue_group(slots, prev_slot, block)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            launches = self.enqueue(slot, prev_slot, block, skip)
+            launches = self.enqueue_group(slots, prev_slot, block, skip)
         return graph, launches
 
     # ---------------------------------------------------------------------------------------

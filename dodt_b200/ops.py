@@ -453,6 +453,46 @@ def correlation(a, b, kernel_size, max_displacement, stride_1, stride_2, pad, ou
     return out
 
 
+def correlation_stream(maps, kernel_size, max_displacement, stride_1, stride_2, pad, outs=None,
+                       max_ctas=0):
+    """outs[j] = correlation(maps[j], maps[j + 1]) for the consecutive frames of a stream
+    (dodt_correlation_stream): maps is a list of [1,H,W,C] float32 CUDA tensors; up to
+    CORR_STREAM_MAX_PAIRS pairs share a launch and the map two pairs have in common is read once."""
+    maps = list(maps)
+    if len(maps) < 2:
+        raise ValueError("correlation_stream needs at least two feature maps")
+    _need_cuda(*maps)
+    first = maps[0]
+    if first.dim() != 4 or first.shape[0] != 1:
+        raise ValueError("feature maps must be [1, H, W, C]")
+    for m in maps:
+        if m.shape != first.shape:
+            raise ValueError("all feature maps must have the same shape")
+        if m.dtype != torch.float32:
+            raise TypeError("correlation expects float32 inputs")
+    if kernel_size % 2 == 0:
+        raise ValueError("kernel_size must be odd")
+    maps = [m.contiguous() for m in maps]
+    _, H, W, C = first.shape
+    oh, ow, oc = correlation_out_shape(H, W, kernel_size, max_displacement, stride_1, stride_2, pad)
+    if outs is None:
+        outs = [torch.empty((1, oh, ow, oc), dtype=torch.float32, device=first.device)
+                for _ in range(len(maps) - 1)]
+    outs = list(outs)
+    if len(outs) != len(maps) - 1:
+        raise ValueError("one output per pair of consecutive maps")
+    _need_cuda(*outs)
+    for o in outs:
+        if tuple(o.shape) != (1, oh, ow, oc) or not o.is_contiguous() or o.dtype != torch.float32:
+            raise ValueError("outputs must be contiguous float32 [1, %d, %d, %d]" % (oh, ow, oc))
+    mp = (ctypes.c_void_p * len(maps))(*[m.data_ptr() for m in maps])
+    op = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+    check(load().dodt_correlation_stream(mp, len(maps), op, H, W, C, kernel_size, max_displacement,
+                                         stride_1, stride_2, pad, int(max_ctas), _stream()),
+          "dodt_correlation_stream")
+    return outs
+
+
 def correlation_grad_workspace_bytes(N, H, W, C, kernel_size, max_displacement, stride_1, stride_2, pad):
     return int(load().dodt_correlation_grad_workspace_bytes(N, H, W, C, kernel_size, max_displacement,
                                                              stride_1, stride_2, pad))

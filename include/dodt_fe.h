@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DODT_FE_VERSION 107 /* major*100 + minor */
+#define DODT_FE_VERSION 108 /* major*100 + minor */
 
 typedef void *dodt_stream_t; /* cudaStream_t */
 
@@ -291,6 +291,19 @@ int dodt_correlation_shared(const float *a, const float *b, int32_t batch, int32
                             int32_t width, int32_t channels, int32_t kernel_size,
                             int32_t max_displacement, int32_t stride_1, int32_t stride_2,
                             int32_t pad, float *out, int32_t max_ctas, dodt_stream_t stream);
+
+/* Frame-stream form of S4 (DODT correlates EVERY pair of adjacent key frames of a sequence,
+ * avod/core/models/dt_rpn_model.py:324-331 called once per sample pair by the inference loop):
+ * outs[j] = correlation(maps[j], maps[j + 1]) for j = 0 .. n_maps - 2, bit-identical to n_maps - 1
+ * calls of dodt_correlation with batch 1. Up to DODT_CORR_STREAM_MAX_PAIRS pairs share one launch
+ * whose tiles are interleaved over the pairs, so that the map two neighbouring pairs have in common
+ * is read from HBM once. maps, outs: HOST arrays of n_maps / n_maps - 1 device pointers
+ * ([1,H,W,C] inputs, [1,out_h,out_w,out_c] outputs). max_ctas as for dodt_correlation_shared. */
+#define DODT_CORR_STREAM_MAX_PAIRS 8
+int dodt_correlation_stream(const float *const *maps, int32_t n_maps, float *const *outs,
+                            int32_t height, int32_t width, int32_t channels, int32_t kernel_size,
+                            int32_t max_displacement, int32_t stride_1, int32_t stride_2,
+                            int32_t pad, int32_t max_ctas, dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * S4 backward — gradients of the correlation w.r.t. both inputs. Replaces the

@@ -27,15 +27,21 @@ streams = [torch.cuda.Stream() for _ in range(n_slots)]
 main = torch.cuda.current_stream()
 
 
+GROUP = int(os.environ.get("ABL_GROUP", "1"))     # consecutive frames per graph (one S4 launch)
+assert n_slots % GROUP == 0 and steps % GROUP == 0
+
+
 def run(skip):
-    graphs = [fe.capture(slots[i], slots[i - 1], None, skip)[0] for i in range(n_slots)]
+    n_groups = n_slots // GROUP
+    graphs = [fe.capture_group(slots[g * GROUP:(g + 1) * GROUP], slots[g * GROUP - 1], None, skip)[0]
+              for g in range(n_groups)]
 
     def rr(n):
         for st in streams:
             st.wait_stream(main)
-        for i in range(n):
-            with torch.cuda.stream(streams[i % n_slots]):
-                graphs[i % n_slots].replay()
+        for i in range(n // GROUP):
+            with torch.cuda.stream(streams[i % n_groups]):
+                graphs[i % n_groups].replay()
         for st in streams:
             main.wait_stream(st)
     rr(3 * n_slots)
