@@ -1,5 +1,5 @@
 """Runs one stage of the front end a few times on synthetic config-B data (for ncu captures).
-usage: python tools/run_stage.py {corr|bev|filter|nms|crops|frame} [reps]"""
+usage: python tools/run_stage.py {corr|corrstream|bev|filter|nms|crops|frame} [reps]"""
 import os
 import sys
 
@@ -27,7 +27,13 @@ fe.enqueue(slots[1], slots[0])
 torch.cuda.synchronize()
 c, s, p = fe.cfg, slots[1], slots[0]
 for _ in range(reps):
-    if what == "corr":
+    if what == "corrstream":   # the frame runner's launch: 4 consecutive pairs, one kernel
+        if "ring" not in globals():
+            ring = [torch.rand_like(s.bev_feat) for _ in range(5)]
+            outs = [torch.empty_like(s.corr) for _ in range(4)]
+        ops.correlation_stream(ring, 1, c.corr_max_displacement, 1, c.corr_stride_2, c.corr_padding, outs=outs,
+                               max_ctas=int(os.environ.get("CORR_CTAS", "0")))
+    elif what == "corr":
         ops.correlation(p.bev_feat, s.bev_feat, 1, c.corr_max_displacement, 1, c.corr_stride_2, c.corr_padding, out=s.corr)
     elif what == "bev":
         ops.bev_slices(s.points[:, :s.n_points], fe.bev_params, s.maps, s.occ, s.stats, s.ws_bev)
