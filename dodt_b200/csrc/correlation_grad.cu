@@ -177,13 +177,29 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, in
 
     __syncthreads();   // the previous tile's last chunk has been consumed
     // ---- coefficients of the tile: each row is a contiguous run of kTW * D2 floats
-#pragma unroll 4
-    for (int e = threadIdx.x; e < kTH * kTW * D2 / GE; e += kThreads) {
-      const int r_ = e / (kTW * D2 / GE), f = (e % (kTW * D2 / GE)) * GE;
-      const int gy = ty0 + r_ - cshift, gx = tx0 + f / D2 - cshift;
-      const bool ok = gy >= 0 && gy < ch && gx >= 0 && gx < cw;
-      const float *src = ok ? cn + (static_cast<size_t>(gy) * cw + gx) * D2 + f % D2 : cn;
-      cp_async<GB>(smem_u32(sg + r_ * Cfg::G_PITCH + f), src, ok);
+    // (a row's copies differ by compile-time offsets from one global and one shared base; the
+    // columns inside the coefficient map are the float range [f_lo, f_hi) of the row)
+    {
+      constexpr int kPerRow = kTW * D2 / GE;                       // copies per tile row
+      constexpr int kIter = (kPerRow + kThreads - 1) / kThreads;
+      const int f_lo = max(0, cshift - tx0) * D2, f_hi = min(kTW, cw + cshift - tx0) * D2;
+      const int f0 = static_cast<int>(threadIdx.x) * GE;
+#pragma unroll
+      for (int r_ = 0; r_ < kTH; ++r_) {
+        const int gy = ty0 + r_ - cshift;
+        const bool row_ok = gy >= 0 && gy < ch;
+        const long long off = (static_cast<long long>(gy) * cw + (tx0 - cshift)) * D2 + f0;
+        const float *src0 = row_ok ? cn + off : cn;                // only dereferenced when ok
+        const uint32_t dst0 = smem_u32(sg + r_ * Cfg::G_PITCH + f0);
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+          const int f = f0 + i * kThreads * GE;
+          if (kPerRow % kThreads == 0 || f < kTW * D2) {
+            const bool ok = row_ok && f >= f_lo && f < f_hi;
+            cp_async<GB>(dst0 + i * kThreads * GE * 4, ok ? src0 + i * kThreads * GE : cn, ok);
+          }
+        }
+      }
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -196,17 +212,34 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, in
     __syncthreads();   // sg is dead: the stages may be filled
 
     // stage the other input's tile with its halo (zero outside the image = padding)
+    // Loader thread (ly, lx) copies the 16-byte pieces lx, lx + 16, ... of tile rows ly, ly + 8, ...:
+    // piece lx + 16 j is half (lx & 1) of pixel (lx >> 1) + 8 j, so the copies of a row differ by
+    // compile-time offsets (8 pixels) from one global and one shared base (adding 8 to a pixel
+    // index leaves the bank swizzle of smem_off unchanged).
+    const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
+    const int lhalf = lx & 1, lpx = lx >> 1;
     auto issue = [&](int chunk) {
       float *sb = smem + (chunk & 1) * Cfg::B_FLOATS;
-      const int c0 = chunk * kCC;
-#pragma unroll 6
-      for (int e = threadIdx.x; e < Cfg::BH * Cfg::BW * 2; e += kThreads) {
-        const int half = e & 1, p = e >> 1;
-        const int py = p / Cfg::BW, px = p % Cfg::BW;
-        const int gy = ty0 + py - Cfg::HALO, gx = tx0 + px - Cfg::HALO;
-        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        const float *src = ok ? on + (static_cast<size_t>(gy) * W + gx) * C + c0 + 4 * half : on;
-        cp_async<16>(smem_u32(sb + smem_off(py * Cfg::BPITCH + px, half)), src, ok);
+      const int c0 = chunk * kCC + 4 * lhalf;
+      constexpr int kRowsPer = (Cfg::BH + kThreads / 16 - 1) / (kThreads / 16);
+      constexpr int kPieces = (Cfg::BW * 2 + 15) / 16;
+      const int gx0 = tx0 - Cfg::HALO + lpx;
+#pragma unroll
+      for (int rr = 0; rr < kRowsPer; ++rr) {
+        const int py = ly + rr * (kThreads / 16);
+        if (Cfg::BH % (kThreads / 16) == 0 || py < Cfg::BH) {
+          const int gy = ty0 + py - Cfg::HALO;
+          const bool row_ok = gy >= 0 && gy < H;
+          const float *src0 = row_ok ? on + (static_cast<long long>(gy) * W + gx0) * C + c0 : on;
+          const uint32_t dst0 = smem_u32(sb + smem_off(py * Cfg::BPITCH + lpx, lhalf));
+#pragma unroll
+          for (int j = 0; j < kPieces; ++j) {
+            if (Cfg::BW * 2 % 16 == 0 || lx + 16 * j < Cfg::BW * 2) {
+              const bool ok = row_ok && static_cast<unsigned>(gx0 + 8 * j) < static_cast<unsigned>(W);
+              cp_async<16>(dst0 + j * 8 * kCC * 4, ok ? src0 + static_cast<long long>(j) * 8 * C : on, ok);
+            }
+          }
+        }
       }
       cp_async_commit();
     };
@@ -257,14 +290,19 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, in
         for (int j = 0; j < kPX; ++j) {
           const int ox = tx0 + x0 + 2 * j;
           if (ox < W) {
-            float4 *d = reinterpret_cast<float4 *>(dn + (static_cast<size_t>(oy) * W + ox) * C + c0);
+            float *d = dn + (static_cast<size_t>(oy) * W + ox) * C + c0;
+            float4 v[2];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              float4 v = acc[j][half];
-              v.x = __fdiv_rn(v.x, sumelems); v.y = __fdiv_rn(v.y, sumelems);
-              v.z = __fdiv_rn(v.z, sumelems); v.w = __fdiv_rn(v.w, sumelems);
-              d[half] = v;
+              v[half] = acc[j][half];
+              v[half].x = __fdiv_rn(v[half].x, sumelems); v[half].y = __fdiv_rn(v[half].y, sumelems);
+              v[half].z = __fdiv_rn(v[half].z, sumelems); v[half].w = __fdiv_rn(v[half].w, sumelems);
             }
+            // one 256-bit store per pixel chunk: the 32-byte sector is written whole (sm_100)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d), "f"(v[0].x),
+                         "f"(v[0].y), "f"(v[0].z), "f"(v[0].w), "f"(v[1].x), "f"(v[1].y), "f"(v[1].z),
+                         "f"(v[1].w)
+                         : "memory");
           }
         }
       }
