@@ -83,6 +83,34 @@ def test_host_only_entry_points(lib):
     assert lib.dodt_nms_state_offset(89600) < ops.nms_workspace_bytes(89600)
     assert lib.dodt_compact_workspace_bytes(89600) > 0
     assert lib.dodt_launch_count() >= 0
+    # S4 backward: workspace = the displacement-flipped copy of the gradient, only for the
+    # kernel_size 1 / stride_1 1 / stride_2 2 family; 0 for invalid or generic parameter sets
+    assert ops.correlation_grad_workspace_bytes(1, 700, 800, 32, 1, 5, 1, 2, 5) == 700 * 800 * 25 * 4
+    assert ops.correlation_grad_workspace_bytes(2, 64, 96, 8, 1, 2, 1, 2, 2) == 2 * 64 * 96 * 9 * 4
+    assert ops.correlation_grad_workspace_bytes(1, 64, 96, 8, 3, 4, 2, 2, 4) == 0
+    assert ops.correlation_grad_workspace_bytes(1, 64, 96, 8, 2, 4, 1, 2, 4) == 0
+
+
+def test_new_entry_points_validate_arguments_on_the_host(lib):
+    """Argument errors are reported before any device work (so they show on a host without a GPU)."""
+    from dodt_b200 import _lib
+    buf = (ctypes.c_float * 8)()
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    one = (ctypes.c_void_p * 1)(ptr)
+    two = (ctypes.c_void_p * 2)(ptr, ptr)
+    # fewer than two maps, a NULL table, a negative CTA cap, an even kernel size
+    assert lib.dodt_correlation_stream(one, 1, one, 8, 8, 8, 1, 2, 1, 2, 2, 0, None) == _lib.DODT_EINVAL
+    assert lib.dodt_correlation_stream(None, 2, one, 8, 8, 8, 1, 2, 1, 2, 2, 0, None) == _lib.DODT_EINVAL
+    assert lib.dodt_correlation_stream(two, 2, one, 8, 8, 8, 1, 2, 1, 2, 2, -1, None) == _lib.DODT_EINVAL
+    assert lib.dodt_correlation_stream(two, 2, one, 8, 8, 8, 2, 2, 1, 2, 2, 0, None) == _lib.DODT_EINVAL
+    assert lib.dodt_correlation_stream(two, 2, one, 4, 64, 8, 1, 8, 1, 2, 0, 0, None) == _lib.DODT_ESHAPE
+    # gradients: both outputs NULL, even kernel size, neighbourhood that does not fit
+    assert lib.dodt_correlation_grad(ptr, ptr, ptr, 1, 8, 8, 8, 1, 2, 1, 2, 2, None, None, None, 0, None) \
+        == _lib.DODT_EINVAL
+    assert lib.dodt_correlation_grad(ptr, ptr, ptr, 1, 8, 8, 8, 2, 2, 1, 2, 2, ptr, ptr, None, 0, None) \
+        == _lib.DODT_EINVAL
+    assert lib.dodt_correlation_grad(ptr, ptr, ptr, 1, 4, 64, 8, 1, 8, 1, 2, 0, ptr, ptr, None, 0, None) \
+        == _lib.DODT_ESHAPE
 
 
 def test_density_lut_matches_reference_formula():
