@@ -407,6 +407,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": "corr_async_k1<2,4,0,8,2> (S4 correlation, %.0f%% of the step's "
                                           "algorithmic bytes)" % (100.0 * abytes["S4"] / abytes["total"]),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8tbs": achieved / 8000.0,
                 "traffic": ncu_traffic(), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": launch_bytes, "pairs_per_launch": G,
                 "launch_us": corr_launch_us,
