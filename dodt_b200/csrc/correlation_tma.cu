@@ -440,14 +440,18 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     const int n = tile % g.batch, sp = tile / g.batch;
     const int tx = sp % g.tiles_x;
     const int ty = sp / g.tiles_x;
+    // DBG & 16: bulk-store epilogue (rows 16-byte aligned in shared memory: pitch +4 instead of +2)
+    constexpr int OUT_PITCH = (DBG & 16) ? kTW * D2 + 4 : Cfg::OUT_PITCH;
+    constexpr int OUT_BYTES = (DBG & 16) ? TH * OUT_PITCH * 4 : Cfg::OUT_BYTES;
+    static_assert(OUT_BYTES <= Cfg::STAGE_BYTES + Cfg::SPARE && OUT_BYTES % 16 == 0, "staging fits a stage");
     float *stg = reinterpret_cast<float *>(
-        smem + (stage == NST - 1 ? stage * Cfg::STAGE1_OFF + Cfg::STAGE_BYTES - Cfg::OUT_BYTES
+        smem + (stage == NST - 1 ? stage * Cfg::STAGE1_OFF + Cfg::STAGE_BYTES - OUT_BYTES
                                  : stage * Cfg::STAGE1_OFF));
     __syncthreads();  // everyone is done reading this stage
     if (g.pow2) {
 #pragma unroll
       for (int j = 0; j < PX; ++j) {
-        float *dst = stg + row * Cfg::OUT_PITCH + (x0 + 2 * j) * D2;
+        float *dst = stg + row * OUT_PITCH + (x0 + 2 * j) * D2;
 #pragma unroll
         for (int k = 0; k < D2; ++k) dst[k] = __fmul_rn(acc[j][k], g.inv_c);   // exact: 1/2^k
       }
@@ -455,7 +459,7 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
       const float sumelems = static_cast<float>(g.C);
 #pragma unroll
       for (int j = 0; j < PX; ++j) {
-        float *dst = stg + row * Cfg::OUT_PITCH + (x0 + 2 * j) * D2;
+        float *dst = stg + row * OUT_PITCH + (x0 + 2 * j) * D2;
 #pragma unroll
         for (int k = 0; k < D2; ++k) dst[k] = __fdiv_rn(acc[j][k], sumelems);
       }
@@ -467,8 +471,25 @@ corr_async_k1(const float *__restrict__ a, const float *__restrict__ b, const Co
     float *gout = out_img + (static_cast<size_t>(ty * TH) * g.out_w + tx * kTW) * D2;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(out_img) % 8 == 0) && ((g.out_w * D2) % 2 == 0) &&
                         (valid_floats % 2 == 0);
-    for (int r = warp; r < ((DBG & 4) ? 0 : valid_rows); r += kWarps) {
-      const float *src = stg + r * Cfg::OUT_PITCH;
+    const bool bulk_ok = (DBG & 16) && reinterpret_cast<uintptr_t>(out_img) % 16 == 0 &&
+                         (g.out_w * D2) % 4 == 0 && valid_floats % 4 == 0;
+    if (bulk_ok) {
+      // one bulk copy (TMA, shared -> global) per tile row, issued by the first valid_rows threads;
+      // the issuing threads wait until the engine has READ the staging rows, the next unit's
+      // __syncthreads then keeps the refill of this stage behind that
+      if (static_cast<int>(threadIdx.x) < valid_rows) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t src = smem_u32(stg + threadIdx.x * OUT_PITCH);
+        float *dstrow = gout + static_cast<size_t>(threadIdx.x) * g.out_w * D2;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstrow), "r"(src),
+                     "r"(valid_floats * 4)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    }
+    for (int r = warp; r < (((DBG & 4) || bulk_ok) ? 0 : valid_rows); r += kWarps) {
+      const float *src = stg + r * OUT_PITCH;
       float *dstrow = gout + static_cast<size_t>(r) * g.out_w * D2;
       if (vec_ok) {
         for (int e = lane; e < valid_floats / 2; e += 32)
@@ -635,6 +656,7 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
     if (r == 2 && dbg == 4) return launch_async<2, 4, 0, 8, 2, 2, 4>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
     if (r == 2 && dbg == 5) return launch_async<2, 4, 0, 8, 2, 2, 5>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
     if (r == 2 && dbg == 6) return launch_async<2, 4, 0, 8, 2, 2, 6>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+    if (r == 2 && dbg == 16) return launch_async<2, 4, 0, 8, 2, 2, 16>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
   }
   // default: 8-row tiles, 4 warps per CTA, TWO CTAs per SM — the per-unit barrier, the exposed
   // tail of the copies and the epilogue of one CTA hide behind the other CTA's math
@@ -656,6 +678,11 @@ int correlation_stream_tma(const float *const *maps, int n_pairs, float *const *
   for (int k = 0; k <= n_pairs; ++k)
     if (reinterpret_cast<uintptr_t>(maps[k]) % 16) return 1;
   if (static_cast<long long>(out_h) * out_w < 1024) return 1;
+  static int dbg = -1;
+  if (dbg < 0) { const char *e = getenv("DODT_CORR_DBG"); dbg = e ? atoi(e) : 0; }
+  if (r == 2 && dbg == 16)
+    return launch_async<2, 4, 0, 8, 2, 2, 16>(nullptr, nullptr, n_pairs, H, W, C, out_h, out_w, shift, nullptr,
+                                              max_ctas, stream, maps, outs);
   switch (r) {
     case 1: return launch_async<1, 4, 0, 8, 2>(nullptr, nullptr, n_pairs, H, W, C, out_h, out_w, shift,
                                                nullptr, max_ctas, stream, maps, outs);
