@@ -26,6 +26,8 @@
 // from L2; no shared-memory staging of pixels is used because a 7x7 crop touches at most 196 of
 // the several hundred pixels under its box (staging the box would read more lines than the gather).
 // The element-per-thread kernel (crop_resize_kernel) remains for tensors beyond 2^31 elements.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dodt {
@@ -121,7 +123,7 @@ crop_resize_kernel(const float *__restrict__ image, const float *__restrict__ bo
 }
 
 constexpr int kCropThreads = 256;
-constexpr int kCropTableMax = 1024;   // axis-table entries per CTA (16 KB)
+constexpr int kCropTableMax = 1024;   // axis-table entries per CTA (16 KB; 2048 entries measured slower: 10.3 k frames/s)
 
 struct CropMulti {
   const float *image[DODT_MAX_CROP_MAPS];
@@ -263,7 +265,12 @@ bool plan_tables(CropMulti *m, int n_specs, int64_t n, unsigned *grid_x) {
     const int cv = m->C[k] / m->vec[k];
     const long long per_roi = static_cast<long long>(S) * cv;
     if (elems >= 0x7FFFFFFFll || per_roi > 65535) return false;
-    int R = static_cast<int>((2 * kCropThreads + per_roi - 1) / per_roi);   // ~512 items per CTA
+    // ~4096 items (16 per thread) per CTA: measured in the frame pipeline, 512 / 1024 / 2048 / 4096 /
+    // 8192 items give 10.50 / 10.62 / 10.70 / 10.88 / 10.80 k frames/s — fewer, longer CTAs cost the
+    // co-running kernels less than many short ones, until too few CTAs are left to balance the SMs
+    static int target = -1;   // DODT_CROP_ITEMS overrides (experiments)
+    if (target < 0) { const char *e = getenv("DODT_CROP_ITEMS"); target = e ? atoi(e) : 16 * kCropThreads; }
+    int R = static_cast<int>((target + per_roi - 1) / per_roi);
     if (R < 1) R = 1;
     if (R > kCropTableMax / axes) R = kCropTableMax / axes;
     while (R > 1 && R * per_roi > 65535) --R;
