@@ -108,14 +108,19 @@ ii_band_prefix(int bands, int nz, const int *__restrict__ bandsum, int *__restri
   }
 }
 
-// one thread per integral-image element: add the offset of its band
+// add its band's offset to every integral-image element: a thread owns one column z of
+// kOffRows consecutive rows (kOffRows divides kBand, so the rows share one band offset)
+constexpr int kOffRows = 8;
+static_assert(kBand % kOffRows == 0, "rows of a CTA lie in one band");
 __global__ void __launch_bounds__(256)
 ii_band_offsets(int nx, int nz, int *__restrict__ ii, const int *__restrict__ bandoff) {
   const int z = blockIdx.x * 256 + threadIdx.x;
-  const int x = blockIdx.y;                   // grid row 0..nx-1 <-> image row x+1
-  if (z >= nz || x < kBand) return;           // band 0 needs no offset
-  const int off = __ldg(bandoff + static_cast<size_t>(x / kBand) * nz + z);
-  if (off) ii[static_cast<size_t>(x + 1) * (nz + 1) + z + 1] += off;
+  const int x0 = blockIdx.y * kOffRows;       // grid rows x0.. <-> image rows x0+1..
+  if (z >= nz || x0 < kBand) return;          // band 0 needs no offset
+  const int off = __ldg(bandoff + static_cast<size_t>(x0 / kBand) * nz + z);
+  if (off == 0) return;
+  const int x1 = min(nx, x0 + kOffRows);
+  for (int x = x0; x < x1; ++x) ii[static_cast<size_t>(x + 1) * (nz + 1) + z + 1] += off;
 }
 
 template <typename T>
@@ -212,7 +217,7 @@ int dodt_integral_image_2d(const uint8_t *occ, int32_t nx, int32_t nz, int32_t *
     int *bandoff = bandsum + static_cast<size_t>(bands) * nz;
     ii_band_prefix<<<ceil_div(nz, 64), 64, 0, stream>>>(bands, nz, bandsum, bandoff);
     DODT_AFTER_LAUNCH();
-    dim3 grid(ceil_div(nz, 256), nx);
+    dim3 grid(ceil_div(nz, 256), ceil_div(nx, kOffRows));
     ii_band_offsets<<<grid, 256, 0, stream>>>(nx, nz, ii, bandoff);
     DODT_AFTER_LAUNCH();
   }
