@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--slots", type=int, default=24)
     ap.add_argument("--group", type=int, default=4,
                     help="consecutive frames per CUDA graph: their correlations share one launch")
+    ap.add_argument("--corr-ctas", type=int, default=None,
+                    help="CTA cap of the correlation launch inside the frame runner (default: FrontEndConfig)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -208,7 +210,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    fe = FrontEnd()
+    from dodt_b200.frontend import FrontEndConfig
+    cfg = FrontEndConfig()
+    if args.corr_ctas is not None:
+        cfg.corr_max_ctas = args.corr_ctas
+    fe = FrontEnd(cfg)
     G = max(1, args.group)
     n_slots = max(2, args.slots)
     n_slots = (n_slots + G - 1) // G * G       # whole groups
