@@ -13,6 +13,7 @@ import pytest
 import torch
 
 from oracle import c_oracle as CO
+from oracle import corr_autograd as AG
 from oracle import np_oracle as O
 
 CASES = [
@@ -38,47 +39,37 @@ def _inputs(shape, kw, seed=0):
     return a, b, g
 
 
-def torch_forward_f64(a, b, kernel_size, max_displacement, stride_1, stride_2, padding):
-    """Independent float64 forward (correlation_kernel.cu.cc:45-110) built from torch slicing so
-    that autograd differentiates it. Inputs are padded by `padding` plus a zero margin that makes
-    every displaced patch addressable."""
-    ks, md, s1, s2, pad = kernel_size, max_displacement, stride_1, stride_2, padding
-    N, H, W, C = a.shape
-    oh, ow, oc = O.correlation_out_shape(H, W, ks, md, s1, s2, pad)
-    r = md // s2
-    wn = 2 * r + 1
-    ex = r * s2 + md + ks + s1 * max(oh, ow)
-    P = pad + ex
-    ap = torch.nn.functional.pad(a, (0, 0, P, P, P, P))
-    bp = torch.nn.functional.pad(b, (0, 0, P, P, P, P))
-    outs = []
-    for k in range(oc):
-        s2o, s2p = (k % wn - r) * s2, (k // wn - r) * s2
-        acc = 0
-        for j in range(ks):
-            for i in range(ks):
-                y0, x0 = md + ex + j, md + ex + i
-                pa = ap[:, y0:y0 + s1 * oh:s1, x0:x0 + s1 * ow:s1]
-                pb = bp[:, y0 + s2p:y0 + s2p + s1 * oh:s1, x0 + s2o:x0 + s2o + s1 * ow:s1]
-                acc = acc + (pa * pb).sum(-1)
-        outs.append(acc / (ks * ks * C))
-    return torch.stack(outs, dim=-1)
-
-
 @pytest.mark.parametrize("shape,kw", CASES)
 def test_oracle_grad_is_the_gradient_of_the_forward(shape, kw):
     a, b, g = _inputs(shape, kw)
-    ta = torch.from_numpy(a).double().requires_grad_(True)
-    tb = torch.from_numpy(b).double().requires_grad_(True)
-    out = torch_forward_f64(ta, tb, **kw)
+    out, want_a, want_b = AG.gradients_f64(a, b, g, **kw)
     # the differentiated forward is the forward the oracle (and the kernels) compute
-    np.testing.assert_allclose(out.detach().numpy(), CO.correlation(a, b, **kw), rtol=1e-5, atol=1e-6)
-    out.backward(torch.from_numpy(g).double())
+    np.testing.assert_allclose(out, CO.correlation(a, b, **kw), rtol=1e-5, atol=1e-6)
     ga, gb = CO.correlation_grad(g, a, b, **kw)
     assert ga.shape == a.shape and gb.shape == b.shape and ga.dtype == np.float32
-    scale = max(np.abs(ta.grad.numpy()).max(), 1e-30)
-    np.testing.assert_allclose(ga, ta.grad.numpy(), rtol=1e-5, atol=2e-6 * scale)
-    np.testing.assert_allclose(gb, tb.grad.numpy(), rtol=1e-5, atol=2e-6 * scale)
+    scale = max(np.abs(want_a).max(), 1e-30)
+    np.testing.assert_allclose(ga, want_a, rtol=1e-5, atol=2e-6 * scale)
+    np.testing.assert_allclose(gb, want_b, rtol=1e-5, atol=2e-6 * scale)
+
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "s4_grad_autograd.npz"))
+
+
+def test_oracle_grad_against_frozen_autograd_vectors():
+    """tests/golden/s4_grad_autograd.npz (python -m oracle.corr_autograd): float64 autograd
+    gradients frozen with their inputs; the C oracle must reproduce them."""
+    gold = _golden()
+    for i in range(len(AG.GOLDEN_CASES)):
+        ks, md, s1, s2, pad = (int(v) for v in gold["attrs%d" % i])
+        kw = dict(kernel_size=ks, max_displacement=md, stride_1=s1, stride_2=s2, padding=pad)
+        a, b, g = gold["a%d" % i], gold["b%d" % i], gold["g%d" % i]
+        np.testing.assert_allclose(CO.correlation(a, b, **kw), gold["out%d" % i], rtol=1e-5, atol=1e-6)
+        ga, gb = CO.correlation_grad(g, a, b, **kw)
+        scale = np.abs(gold["ga%d" % i]).max()
+        np.testing.assert_allclose(ga, gold["ga%d" % i], rtol=1e-5, atol=2e-6 * scale)
+        np.testing.assert_allclose(gb, gold["gb%d" % i], rtol=1e-5, atol=2e-6 * scale)
 
 
 def test_oracle_grad_adjoint_identity():
@@ -120,6 +111,17 @@ def test_gpu_correlation_grad_matches_oracle(dd, shape, kw):
     got_a, got_b = dd.correlation_grad(g, a, b, **kw2)
     np.testing.assert_array_equal(got_a, want_a)
     np.testing.assert_array_equal(got_b, want_b)
+
+
+@pytest.mark.gpu
+def test_gpu_correlation_grad_against_frozen_autograd_vectors(dd):
+    gold = _golden()
+    for i in range(len(AG.GOLDEN_CASES)):
+        ks, md, s1, s2, pad = (int(v) for v in gold["attrs%d" % i])
+        ga, gb = dd.correlation_grad(gold["g%d" % i], gold["a%d" % i], gold["b%d" % i], ks, md, s1, s2, pad)
+        scale = np.abs(gold["ga%d" % i]).max()
+        np.testing.assert_allclose(ga, gold["ga%d" % i], rtol=1e-5, atol=2e-6 * scale)
+        np.testing.assert_allclose(gb, gold["gb%d" % i], rtol=1e-5, atol=2e-6 * scale)
 
 
 @pytest.mark.gpu
