@@ -418,12 +418,14 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": launch_bytes, "pairs_per_launch": G,
                 "launch_us": corr_launch_us,
                 "launch": "as the frame runner launches it: the %d frame pairs of a group in one "
-                          "frame-stream launch (a map shared by two pairs is read from HBM once), %d "
-                          "persistent CTAs (one per SM), the rest of each SM left to the other stages "
-                          "of neighbouring frames" % (G, c.corr_max_ctas),
+                          "frame-stream launch (a map shared by two pairs is read from HBM once), %s"
+                          % (G, ("%d persistent CTAs, the rest of each SM left to the other stages of "
+                                 "neighbouring frames" % c.corr_max_ctas) if c.corr_max_ctas else
+                             "296 persistent CTAs (two per SM)"),
                 "standalone": {"us": corr_alone_us, "achieved": launch_bytes / (corr_alone_us * 1e-6) / 1e9,
                                "frac": launch_bytes / (corr_alone_us * 1e-6) / 1e9 / peak,
-                               "launch": "the same launch with 296 CTAs (two per SM), nothing else running"},
+                               "launch": "the same launch without a CTA cap (296 CTAs, two per SM), "
+                                         "nothing else running"},
                 "frame": {"algorithmic_bytes": abytes["total"],
                           "achieved": abytes["total"] * fps / world / 1e9,
                           "frac": abytes["total"] * fps / world / 1e9 / peak},

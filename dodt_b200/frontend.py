@@ -52,8 +52,13 @@ class FrontEndConfig:
     corr_padding: int = 5
     corr_stride_2: int = 2
     nms_max_windows: int = 4                        # launches reserved for the RPN NMS in a graph
-    corr_max_ctas: int = 148                        # one persistent correlation CTA per SM: the
-                                                    # other half of each SM runs neighbouring frames
+    corr_max_ctas: int = 0                          # CTA cap of the correlation launch (0 = none: two
+                                                    # persistent CTAs per SM). 148 (one per SM, the other
+                                                    # half of each SM left to neighbouring frames) is ~2 %
+                                                    # faster in the frame pipeline when the hardware
+                                                    # spreads the 148 CTAs one per SM, but about one run
+                                                    # in ten it co-locates some of them and the launch
+                                                    # takes 1.5x (330 vs 224 us for four pairs)
 
 
 def _layout(specs, align=256):
