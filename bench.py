@@ -11,7 +11,7 @@ and occupancy, 89 600-anchor filter, 3x3 RPN crops, NMS 0.8/1024, tau=1 BEV-feat
 KITTI-shaped data. `value` is timed with every input resident in HBM: CUDA graphs of --group
 consecutive frames (their correlations are one frame-stream launch) replayed round-robin over
 --slots resident frame slots on one stream per group, so that each step reads inputs the previous
-steps did not touch (24 slots x 135 MB > the 126 MB L2); `e2e` re-times the same steps through the
+steps did not touch (32 slots x 135 MB > the 126 MB L2); `e2e` re-times the same steps through the
 public Python API with all inputs in pinned host memory, H2D and D2H inside the timed region.
 """
 import argparse
@@ -37,8 +37,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--slots", type=int, default=24)
-    ap.add_argument("--group", type=int, default=4,
+    ap.add_argument("--slots", type=int, default=32)
+    ap.add_argument("--group", type=int, default=8,
                     help="consecutive frames per CUDA graph: their correlations share one launch")
     ap.add_argument("--corr-ctas", type=int, default=None,
                     help="CTA cap of the correlation launch inside the frame runner (default: FrontEndConfig)")

@@ -27,10 +27,11 @@ fe.enqueue(slots[1], slots[0])
 torch.cuda.synchronize()
 c, s, p = fe.cfg, slots[1], slots[0]
 for _ in range(reps):
-    if what == "corrstream":   # the frame runner's launch: 4 consecutive pairs, one kernel
+    if what == "corrstream":   # the frame runner's launch: CORR_PAIRS (8) consecutive pairs, one kernel
         if "ring" not in globals():
-            ring = [torch.rand_like(s.bev_feat) for _ in range(5)]
-            outs = [torch.empty_like(s.corr) for _ in range(4)]
+            n_pairs = int(os.environ.get("CORR_PAIRS", "8"))
+            ring = [torch.rand_like(s.bev_feat) for _ in range(n_pairs + 1)]
+            outs = [torch.empty_like(s.corr) for _ in range(n_pairs)]
         ops.correlation_stream(ring, 1, c.corr_max_displacement, 1, c.corr_stride_2, c.corr_padding, outs=outs,
                                max_ctas=int(os.environ.get("CORR_CTAS", "0")))
     elif what == "corr":
