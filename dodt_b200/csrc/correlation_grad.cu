@@ -331,32 +331,43 @@ corr_grad_flip(const float *__restrict__ grad, int out_h, int out_w, int H, int 
   const float *gn = grad + static_cast<size_t>(n) * out_h * out_w * D2;
   float *fn = gf + static_cast<size_t>(n) * H * W * D2;
   const int gx0 = tx0 - HALO - shift;
+  // source offset of displacement k' relative to its own pixel: rows 2p', columns 2o', element D2-1-k'
+  __shared__ int lut[D2];
+  if (threadIdx.x < D2) {
+    const int k = threadIdx.x;
+    lut[k] = 2 * (k / WN) * PITCH + 2 * (k % WN) * D2 + (D2 - 1 - k);
+  }
+  // columns inside the gradient map = the float range [f_lo, f_hi) of a staged row
+  const int f_lo = max(0, -gx0) * D2, f_hi = min(SW, out_w - gx0) * D2;
 #pragma unroll 4
   for (int e = threadIdx.x; e < SH * SW * D2 / GE; e += kFlipThreads) {
-    const int r_ = e / (SW * D2 / GE), f = (e % (SW * D2 / GE)) * GE;
-    const int gy = ty0 + r_ - HALO - shift, gx = gx0 + f / D2;
-    const bool ok = gy >= 0 && gy < out_h && gx >= 0 && gx < out_w;
+    const int r_ = e / (SW * D2 / GE), f = (e - r_ * (SW * D2 / GE)) * GE;
+    const int gy = ty0 + r_ - HALO - shift;
+    const bool ok = gy >= 0 && gy < out_h && f >= f_lo && f < f_hi;
     const float *src = ok ? gn + (static_cast<long long>(gy) * out_w + gx0) * D2 + f : gn;
     cp_async<4 * GE>(smem_u32(smem + r_ * PITCH + f), src, ok);
   }
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
-  auto pick = [&](int r_, int f) {
-    const int px = f / D2, k = f % D2;
-    const int p = k / WN, o = k % WN;   // p' + R, o' + R
-    return smem[(r_ + 2 * p) * PITCH + (px + 2 * o) * D2 + (D2 - 1 - k)];
-  };
   for (int e = threadIdx.x; e < kFH * kFW * D2 / GE; e += kFlipThreads) {
-    const int r_ = e / (kFW * D2 / GE), f = (e % (kFW * D2 / GE)) * GE;
-    const int y = ty0 + r_, x = tx0 + f / D2;
-    if (y >= H || x >= W) continue;
+    const int r_ = e / (kFW * D2 / GE), f = (e - r_ * (kFW * D2 / GE)) * GE;
+    int px = f / D2, k = f - px * D2;
+    const int y = ty0 + r_;
+    if (y >= H || tx0 + px >= W) continue;
     float *d = fn + (static_cast<long long>(y) * W + tx0) * D2 + f;
+    int base = r_ * PITCH + px * D2;
     if constexpr (VEC) {
       // W % 4 == 0 and tx0 % 4 == 0: the four floats lie in columns < W together
-      *reinterpret_cast<float4 *>(d) = make_float4(pick(r_, f), pick(r_, f + 1), pick(r_, f + 2), pick(r_, f + 3));
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i] = smem[base + lut[k]];
+        if (++k == D2) { k = 0; base += D2; }
+      }
+      *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
-      *d = pick(r_, f);
+      *d = smem[base + lut[k]];
     }
   }
 }
