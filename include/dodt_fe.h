@@ -285,8 +285,9 @@ int dodt_correlation(const float *a, const float *b, int32_t batch, int32_t heig
                      dodt_stream_t stream);
 /* The same, for a caller that runs other work next to it: max_ctas > 0 caps the number of
  * (persistent) CTAs of the launch, e.g. one per SM instead of two, which leaves half of every SM's
- * registers and shared memory to kernels of other streams (the frame-stream runner overlaps the
- * latency-bound stages of neighbouring frames with the correlation this way). 0 = no cap. */
+ * registers and shared memory to kernels of other streams. The block scheduler does not promise one
+ * CTA per SM for such a launch: when it co-locates some of them the launch takes up to 1.5x, which is
+ * why the frame-stream runner leaves the cap off by default. 0 = no cap. */
 int dodt_correlation_shared(const float *a, const float *b, int32_t batch, int32_t height,
                             int32_t width, int32_t channels, int32_t kernel_size,
                             int32_t max_displacement, int32_t stride_1, int32_t stride_2,
