@@ -44,7 +44,8 @@ int oracle_correlation(const float *a, const float *b, int N, int H, int W, int 
               if (by < 0 || by >= H || bx < 0 || bx >= W) continue; /* zero padding of B */
               const float *pa = a + (((size_t)n * H + ay) * W + ax) * C;
               const float *pb = b + (((size_t)n * H + by) * W + bx) * C;
-              for (int ch = 0; ch < C; ++ch) lane[ch & 31] += pa[ch] * pb[ch];
+              /* sum[ch_off] += patch * b (correlation_kernel.cu.cc:93) is one FFMA under nvcc's default -fmad=true */
+              for (int ch = 0; ch < C; ++ch) lane[ch & 31] = fmaf(pa[ch], pb[ch], lane[ch & 31]);
             }
           float total = 0.0f;
           for (int t = 0; t < 32; ++t) total += lane[t];

@@ -362,7 +362,8 @@ def correlation(input_a, input_b, kernel_size=1, max_displacement=20, stride_1=1
     as pad.cu.cc:14-74 does; signature of avod/core/corr_layers/correlation.py:7.
 
     Summation order of the kernel is kept: lane t of the 32-thread block accumulates, over the
-    kernel window (j, i) and channels ch = t, t+32, ..., its products in fp32; thread 0 then adds
+    kernel window (j, i) and channels ch = t, t+32, ..., its products in fp32 (fused multiply-adds,
+    as the compiled reference kernel does); thread 0 then adds
     the 32 partial sums in lane order and divides by kernel_size^2 * C.
     """
     f32 = np.float32
@@ -396,10 +397,14 @@ def correlation(input_a, input_b, kernel_size=1, max_displacement=20, stride_1=1
             for i in range(ks):
                 pa = ap[:, ys[:, None] + j, xs[None, :] + i]                     # (N,oh,ow,C)
                 pb = bp[:, ys[:, None] + j + s2p, xs[None, :] + i + s2o]
-                prod = pa * pb
+                # `sum[ch_off] += patch * b` (correlation_kernel.cu.cc:93) compiles to one FFMA (nvcc's
+                # default -fmad=true; pinned by tests/golden/s4_reference_kernel.npz): the fp32 product
+                # is exact in float64, so one float64 add + one rounding to fp32 is the fused result
+                prod = pa.astype(np.float64) * pb.astype(np.float64)
                 for c0 in range(0, C, lanes):
                     chunk = prod[..., c0:c0 + lanes]
-                    partial[..., :chunk.shape[-1]] += chunk
+                    w = chunk.shape[-1]
+                    partial[..., :w] = (chunk + partial[..., :w].astype(np.float64)).astype(f32)
         total = np.zeros((N, oh, ow), dtype=f32)
         for t in range(lanes):
             total = total + partial[..., t]

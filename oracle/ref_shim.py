@@ -4,15 +4,37 @@ Puts the read-only checkout (default /root/reference, override with DODT_REFEREN
 vendored wavedata on sys.path and injects a stub `tensorflow` module so that
 avod.core.{anchor_filter,anchor_projector,box_3d_encoder}, avod.core.bev_generators.bev_slices and
 avod.core.anchor_generators.grid_anchor_3d_generator import under NumPy 2 without TensorFlow.
-The checkout does not exist on the GPU box: everything that uses this module must be skipped when
-`available()` is False (the committed fixtures under tests/golden/ take over there).
+The checkout does not exist on the GPU box; the S1/S2 closure staged by oracle/build_oracle.py
+(oracle/_ref/py) is used there. Everything that uses this module must be skipped when
+`available()` is False (the committed fixtures under tests/golden/ take over), and whatever needs
+more than S1/S2 when `full_checkout()` is False.
 """
 import importlib.machinery
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DODT_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "py")
+
+
+def _root():
+    """The read-only checkout where it exists; otherwise the copy of the S1/S2 modules that
+    oracle/build_oracle.py staged into git-ignored oracle/_ref/py (it travels to the GPU box)."""
+    env = os.environ.get("DODT_REFERENCE_ROOT")
+    for cand in (env, "/root/reference", _STAGED):
+        if cand and os.path.isdir(os.path.join(cand, "avod", "core")) and \
+                os.path.isdir(os.path.join(cand, "wavedata", "wavedata")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _root()
+
+
+def full_checkout():
+    """True when the whole reference tree (anchor generators, projector, fixtures ...) is there,
+    not only the staged S1/S2 modules."""
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "avod", "core", "anchor_generators"))
 
 
 def available():
