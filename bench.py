@@ -5,14 +5,17 @@ correlation + NMS) on N B200s, with the HBM roofline of the dominant kernel and 
   python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K --warmup W   (CPU oracle arm)
 
-A "step" is one frame of BASELINE.json configs[1] (KITTI car config: 120k-point cloud -> 6 BEV maps
-and occupancy, 89 600-anchor filter, 3x3 RPN crops, NMS 0.8/1024, tau=1 BEV-feature correlation,
-7x7 crops of BEV/image/correlation maps for 1024 proposals, NMS 0.01/100) on synthetic
-KITTI-shaped data. `value` is timed with every input resident in HBM: CUDA graphs of --group
-consecutive frames (their correlations are one frame-stream launch) replayed round-robin over
---slots resident frame slots on one stream per group, so that each step reads inputs the previous
-steps did not touch (32 slots x 135 MB > the 126 MB L2); `e2e` re-times the same steps through the
-public Python API with all inputs in pinned host memory, H2D and D2H inside the timed region.
+A "step" is ONE SWEEP of the --slots resident frame slots (32 frames by default) of BASELINE.json
+configs[1] (KITTI car config: 120k-point cloud -> 6 BEV maps and occupancy, 89 600-anchor filter,
+3x3 RPN crops, NMS 0.8/1024, tau=1 BEV-feature correlation, 7x7 crops of BEV/image/correlation maps
+for 1024 proposals, NMS 0.01/100) on synthetic KITTI-shaped data; `value` stays in frames/s
+(= steps x slots x ranks / timed region) and ms_per_step x steps is the timed region. `value` is
+timed with every input resident in HBM: CUDA graphs of --group consecutive frames (their
+correlations are one frame-stream launch) replayed round-robin over the resident slots on one
+stream per group, so that each frame reads inputs the previous frames did not touch (32 slots x
+135 MB > the 126 MB L2), followed by the shard's ONE collective (all_gather of the detection lists);
+`e2e` re-times the same frames through the public Python API with all inputs in pinned host
+memory, H2D and D2H inside the timed region.
 """
 import argparse
 import json
@@ -34,8 +37,8 @@ WORKLOAD = ("configs[1] KITTI car config + tau=1 correlation: 120k pts -> BEV 70
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60, help="sweeps of the resident slots (32 frames each)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--slots", type=int, default=32)
     ap.add_argument("--group", type=int, default=8,
@@ -53,21 +56,25 @@ def parse():
 
 def cpu_arm(steps, warmup, workers):
     """Each step = `workers` frames run concurrently, one frame per process (the reference's own
-    parallelism is os.fork over sample indices, scripts/preprocessing/gen_tracking_mini_batches.py:48-69)."""
+    parallelism is os.fork over sample indices, scripts/preprocessing/gen_tracking_mini_batches.py:48-69).
+    S1/S2 run the reference's OWN NumPy (BevSlices.generate_bev, get_empty_anchor_filter_2d) where
+    the checkout or its staged copy (oracle/_ref/py, built by __graft_entry__.build) is present, else
+    the NumPy restatement; S3/S4/S5 are TF/GPU ops in the reference: C restatement."""
     import multiprocessing as mp
     from oracle import build_oracle, cpu_frontend
     build_oracle.build()
+    use_ref = cpu_frontend.reference_s1_s2_available()
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
         frame = 0
         for _ in range(warmup):
-            pool.map(cpu_frontend._worker, [(CONFIG_ID, frame + i) for i in range(workers)])
+            pool.map(cpu_frontend._worker, [(CONFIG_ID, frame + i, use_ref) for i in range(workers)])
             frame += workers
         t0 = time.perf_counter()
         compute_s = 0.0
         stage = {}
         for _ in range(steps):
-            res = pool.map(cpu_frontend._worker, [(CONFIG_ID, frame + i) for i in range(workers)])
+            res = pool.map(cpu_frontend._worker, [(CONFIG_ID, frame + i, use_ref) for i in range(workers)])
             frame += workers
             compute_s += max(r[0] for r in res)
             for r in res:
@@ -77,7 +84,21 @@ def cpu_arm(steps, warmup, workers):
     n_frames = steps * workers
     # frames/s of the front end itself: input synthesis inside the workers is not counted
     return dict(fps=n_frames / compute_s, wall_s=wall, compute_s=compute_s, frames=n_frames,
-                stage_ms={k: 1e3 * v / n_frames for k, v in stage.items()})
+                stage_ms={k: 1e3 * v / n_frames for k, v in stage.items()}, use_ref=use_ref)
+
+
+def cpu_baseline_object(r, workers, steps):
+    kinds = {"S1": "reference" if r["use_ref"] else "port", "S2": "reference" if r["use_ref"] else "port",
+             "S3": "port", "S4": "port", "S5": "port"}
+    return {"value": r["fps"], "unit": "frames/s", "cores": workers, "kind": "port",
+            "kind_by_stage": kinds,
+            "sample": "%d frames of the same workload (%d steps x %d processes, one frame each); S1/S2 = %s, "
+                      "S3/S4/S5 = C restatement (TF/GPU-only ops in the reference; S4 pinned bit for bit to "
+                      "the reference's CUDA kernels)" %
+                      (r["frames"], steps, workers,
+                       "the reference's own NumPy (BevSlices.generate_bev, get_empty_anchor_filter_2d)"
+                       if r["use_ref"] else "NumPy restatement of the reference's NumPy"),
+            "stage_ms_per_frame": r["stage_ms"]}
 
 
 def run_reference(args):
@@ -95,11 +116,7 @@ def run_reference(args):
         "ms_per_step": 1e3 * r["compute_s"] / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "step": "%d frames in parallel, one per process" % workers},
-        "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": workers, "kind": "port",
-                         "sample": "%d frames (%d steps x %d processes); S1/S2 NumPy restatement of "
-                                   "the reference's NumPy, S3/S4/S5 C restatement" %
-                                   (r["frames"], steps, workers),
-                         "stage_ms_per_frame": r["stage_ms"]},
+        "cpu_baseline": cpu_baseline_object(r, workers, steps),
         "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -224,7 +241,10 @@ def run_ours(args):
     hosts = [HostFrame(fe).fill(synth.frame_inputs(CONFIG_ID, 1000 * rank + i), sequence=rank, frame=i)
              for i in range(n_slots)]
     # this shard's detection lists: one fixed-size row block per frame, gathered ONCE at the end
-    block = shard.DetectionBlock(max(args.steps, 1), fe.cfg.avod_nms_size, dev)
+    K, Wm = max(args.steps, 1), max(args.warmup, 3)
+    F = K * n_slots                            # frames of the timed region: K sweeps of the slots
+    block = shard.DetectionBlock(F, fe.cfg.avod_nms_size, dev)
+    block.gather_buffer(world)                 # receive buffer of the one collective, allocated up front
     n_points = hosts[0].n_points
     for s_, h in zip(slots, hosts):
         h.upload(s_)
@@ -236,13 +256,6 @@ def run_ours(args):
     for g_ in range(n_groups):
         gr, launches = fe.capture_group(slots[g_ * G:(g_ + 1) * G], slots[g_ * G - 1], block)
         graphs.append(gr)
-    singles = {}
-    launches_single = launches // G
-
-    def single(i):
-        if i not in singles:
-            singles[i], _ = fe.capture(slots[i], slots[i - 1], block)
-        return singles[i]
     torch.cuda.synchronize()
 
     def barrier():
@@ -254,36 +267,33 @@ def run_ours(args):
     # Frames of a stream are independent (a slot only READS its predecessor's feature map), so
     # each resident slot replays its graph on its own CUDA stream: the latency-bound stages of one
     # frame (NMS, scans, compaction) overlap the bandwidth-bound stages of its neighbours.
-    K, Wm = args.steps, max(args.warmup, 3)
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_groups)]
     main = torch.cuda.current_stream()
-    for i in range(K % G):      # the tail graphs are captured before anything is timed
-        single(((K // G) % n_groups) * G + i)
 
-    def replay_round_robin(n):
-        """exactly n frames: n // G group replays, then n % G single frames of the next group"""
+    def replay_sweeps(n):
+        """n sweeps of the resident slots = n * n_slots frames: every group graph n times, each
+        group on its own stream"""
         for st in streams:
             st.wait_stream(main)
-        q, r = divmod(n, G)
-        for i in range(q):
-            with torch.cuda.stream(streams[i % n_groups]):
-                graphs[i % n_groups].replay()
-        with torch.cuda.stream(streams[q % n_groups]):
-            for i in range(r):
-                single((q % n_groups) * G + i).replay()
+        for _ in range(n):
+            for g_ in range(n_groups):
+                with torch.cuda.stream(streams[g_]):
+                    graphs[g_].replay()
         for st in streams:
             main.wait_stream(st)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    replay_round_robin(Wm)
+    replay_sweeps(Wm)
+    if world > 1:
+        shard.all_gather_blocks(block)     # warm the communicator up outside the timed region
     barrier()
     if rank == 0:
         # nvidia-smi needs a moment to start: keep the GPU under the same load until it reports
         t_wait = time.time()
         while not sampler.rows and time.time() - t_wait < 3.0:
-            replay_round_robin(n_slots * 20)
+            replay_sweeps(20)
             torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gathered = None
@@ -291,9 +301,9 @@ def run_ours(args):
     barrier()
     w0 = time.time()
     ev0.record()
-    replay_round_robin(K)
-    # the only collective of the path: the shard's detection lists, K frames x 100
-    # rows x 6 floats per rank, inside the timed region
+    replay_sweeps(K)
+    # the only collective of the path: the shard's detection lists, F frames x 100
+    # rows x 6 floats (+ counts, frame ids) per rank in ONE all_gather_into_tensor, inside the timed region
     gathered = shard.all_gather_blocks(block)
     ev1.record()
     barrier()
@@ -305,7 +315,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    fps = K * world / (ms_max / 1e3)
+    fps = F * world / (ms_max / 1e3)
     # single-stream latency of one frame, for reference
     torch.cuda.synchronize()
     la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -318,7 +328,7 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ per-stage + dominant kernel
     c = fe.cfg
-    reps = max(20, min(K, 100))
+    reps = max(20, min(F, 100))
 
     def time_stage(fn):
         """Mean device time of one stage: the stage is captured into a CUDA graph per slot (so the
@@ -410,11 +420,17 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     launch_bytes = G * abytes["S4"]                 # 199.36 MB per pair x G pairs per launch
     achieved = launch_bytes / (corr_launch_us * 1e-6) / 1e9
+    traffic = ncu_traffic()
     roofline = {"bound": "hbm", "kernel": "corr_async_k1<2,4,0,8,2> (S4 correlation, %.0f%% of the step's "
                                           "algorithmic bytes)" % (100.0 * abytes["S4"] / abytes["total"]),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8tbs": achieved / 8000.0,
-                "traffic": ncu_traffic(), "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
+                "frac_algorithmic": achieved / peak,
+                "frac_traffic": (traffic / (corr_launch_us * 1e-6) / 1e9 / peak) if traffic else None,
+                "frac_note": "frac = SURVEY 8(d) algorithmic bytes (both inputs of every pair) / launch time / peak; "
+                             "frac_traffic = DRAM bytes ncu measured for the same launch (each shared map crosses "
+                             "HBM once) / launch time / peak",
                 "algorithmic_bytes_per_launch": launch_bytes, "pairs_per_launch": G,
                 "launch_us": corr_launch_us,
                 "launch": "as the frame runner launches it: the %d frame pairs of a group in one "
@@ -435,7 +451,7 @@ def run_ours(args):
     # Every step: H2D of the frame's inputs from pinned host memory (one packed sensor buffer +
     # the four feature maps), the frame's share of its group graph, D2H of the packed results — all
     # on the group's own stream, so the copies of one group overlap the kernels of its neighbours.
-    e2e = None
+    e2e = e2e_sensor = None
     if not args.no_e2e:
         h2d = hosts[0].h2d_bytes
         d2h = hosts[0].result_buf.numel()
@@ -483,22 +499,27 @@ def run_ours(args):
                 dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
             return float(t_ms.item())
 
-        Ke = max(2 * G, min(K, 60) // G * G)
+        Ke = max(2 * G, min(F, 64) // G * G)
         ems = timed_e2e(Ke, True)
         e2e = {"value": Ke * world / (ems / 1e3), "unit": "frames/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+               "h2d_bytes_per_step": h2d * n_slots, "d2h_bytes_per_step": d2h * n_slots,
+               "h2d_bytes_per_frame": h2d, "d2h_bytes_per_frame": d2h, "frames": Ke,
                "h2d_gbs": h2d * Ke / (ems / 1e3) / 1e9,
                "note": "every slot input (points, BEV/image features, RPN head outputs) copied from "
                        "pinned host memory each step; detection lists copied back; PCIe-bound"}
         # the same with the network feature maps left on the device (where the reference has them:
         # they are TF GPU tensors); only sensor data and head outputs cross PCIe
-        Ks = max(2 * G, min(K, 600) // G * G)
+        Ks = max(2 * G, min(F, 640) // G * G)
         sms = timed_e2e(Ks, False)
-        e2e["sensor_only"] = {
-            "value": Ks * world / (sms / 1e3), "unit": "frames/s", "steps": Ks,
-            "h2d_bytes_per_step": hosts[0].sensor_buf.numel(), "d2h_bytes_per_step": d2h,
-            "note": "points + RPN/AVOD head outputs from pinned host memory each step; BEV/image "
-                    "feature maps resident on the device"}
+        e2e_sensor = {
+            "value": Ks * world / (sms / 1e3), "unit": "frames/s", "frames": Ks,
+            "h2d_bytes_per_step": hosts[0].sensor_buf.numel() * n_slots, "d2h_bytes_per_step": d2h * n_slots,
+            "h2d_bytes_per_frame": hosts[0].sensor_buf.numel(), "d2h_bytes_per_frame": d2h,
+            "note": "what crosses PCIe in the reference too: points + RPN/AVOD head outputs from pinned "
+                    "host memory each frame, detection lists back; the BEV/image feature maps stay on the "
+                    "device, where the reference has them (TF GPU tensors). The full-feature `e2e` above "
+                    "moves 127 MB of network activations per frame over PCIe and is host-memory-bound "
+                    "(it does not scale past 2 GPUs of one box: all GPUs share one root complex / NUMA node)"}
 
     # ------------------------------------------------------------------ cpu baseline (rank 0, N=1)
     cpu = None
@@ -506,19 +527,18 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         workers = max(1, min(cores, 64))
         r = cpu_arm(2, 0, workers)
-        cpu = {"value": r["fps"], "unit": "frames/s", "cores": workers, "kind": "port",
-               "sample": "%d frames of the same workload, one per process; S1/S2 NumPy restatement "
-                         "of the reference's NumPy, S3/S4/S5 C restatement (reference S3-S5 are "
-                         "TF/GPU-only)" % r["frames"],
-               "stage_ms_per_frame": r["stage_ms"]}
+        cpu = cpu_baseline_object(r, workers, 2)
 
     if rank == 0:
         line = {
             "metric": "front-end frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world,
-            "steps": K, "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True,
+            "steps": K, "warmup": Wm, "ms_per_step": ms_max / K, "frames_per_step": n_slots,
+            "frames_timed": F * world, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 binning/predicates, i32 counts)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points": n_points, "anchors": fe.num_anchors,
+            "config": {"workload": WORKLOAD,
+                       "step": "one sweep of the %d resident frame slots = %d frames per GPU" % (n_slots, n_slots),
+                       "points": n_points, "anchors": fe.num_anchors,
                        "anchors_kept": n_kept, "proposals": n_top,
                        "l2": "inputs %.0f MB/step cycled over %d resident frame slots (> 126 MB L2)"
                              % (hosts[0].h2d_bytes / 1e6, n_slots),
@@ -526,8 +546,9 @@ def run_ours(args):
                        "parallelism": "one frame stream per GPU, no data-path collective; one "
                                       "all_gather of detection lists per shard"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches * (K // G) + launches_single * (K % G),
-            "launches_per_step": launches / G, "clocks": clocks,
+            "e2e_sensor_only": e2e_sensor,
+            "gpu_launches": launches * n_groups * K,
+            "launches_per_frame": launches / G, "clocks": clocks,
             "group_latency_us_single_stream": group_latency_us, "frames_per_graph": G,
             "streams": n_groups,
             "gathered": {"ranks": len(gathered), "frames_per_rank": int(block.rows.shape[0]),

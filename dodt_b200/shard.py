@@ -72,14 +72,34 @@ def plan(sequence_lengths, world_size, rank):
 class DetectionBlock:
     """Fixed-size padded detection lists of one shard: rows [frames, max_det, DET_COLS] f32,
     counts [frames] i32, frame_ids [frames, 2] i32 (sequence, frame). Fixed shapes so that the
-    gather is ONE collective of equal-size blocks, whatever each frame detected."""
+    gather is ONE collective of equal-size blocks, whatever each frame detected: the three arrays
+    are views of ONE contiguous 4-byte-word buffer (`buf`), which is what crosses NVLink."""
 
     def __init__(self, max_frames, max_det, device):
-        self.rows = torch.zeros((max_frames, max_det, DET_COLS), dtype=torch.float32, device=device)
-        self.counts = torch.zeros((max_frames,), dtype=torch.int32, device=device)
-        self.frame_ids = torch.full((max_frames, 2), -1, dtype=torch.int32, device=device)
+        self.max_frames, self.max_det = int(max_frames), int(max_det)
+        n_rows = self.max_frames * self.max_det * DET_COLS
+        self._n_rows, self._n_counts, self._n_ids = n_rows, self.max_frames, 2 * self.max_frames
+        self.buf = torch.zeros((n_rows + self._n_counts + self._n_ids,), dtype=torch.float32, device=device)
+        self.rows, self.counts, self.frame_ids = self.views(self.buf)
+        self.frame_ids.fill_(-1)
         self.cursor = torch.zeros((1,), dtype=torch.int32, device=device)   # device-side row cursor
         self.n = 0
+        self._gather_buf = None
+
+    def views(self, buf):
+        """(rows, counts, frame_ids) views of a buffer laid out like `buf`."""
+        a, b = self._n_rows, self._n_rows + self._n_counts
+        rows = buf[:a].view(self.max_frames, self.max_det, DET_COLS)
+        counts = buf[a:b].view(torch.int32)
+        ids = buf[b:b + self._n_ids].view(torch.int32).view(self.max_frames, 2)
+        return rows, counts, ids
+
+    def gather_buffer(self, world):
+        """The receive buffer of the gather, allocated once (outside any timed region)."""
+        if self._gather_buf is None or self._gather_buf.shape[0] != world:
+            self._gather_buf = torch.empty((world, self.buf.numel()), dtype=self.buf.dtype,
+                                           device=self.buf.device)
+        return self._gather_buf
 
     def reset(self):
         """Forget every stored frame (device-side cursor included); no synchronisation."""
@@ -108,18 +128,16 @@ class DetectionBlock:
 
 
 def all_gather_blocks(block, group=None):
-    """The ONE collective of a shard: all_gather of every rank's block (rows, counts, frame ids).
-    Returns [(rows, counts, frame_ids)] per rank, on the block's device, without synchronising;
-    with no process group (or a world of one) it is the local block."""
+    """The ONE collective of a shard: a single all_gather_into_tensor of every rank's packed block
+    (rows, counts and frame ids travel in one buffer; the receive buffer is preallocated by
+    `block.gather_buffer`). Returns [(rows, counts, frame_ids)] per rank as views, on the block's
+    device, without synchronising; with no process group (or a world of one) it is the local block."""
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
         return [(block.rows, block.counts, block.frame_ids)]
     world = dist.get_world_size(group)
-    gathered = []
-    for t in (block.rows, block.counts, block.frame_ids):
-        bufs = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(bufs, t.contiguous(), group=group)
-        gathered.append(bufs)
-    return list(zip(*gathered))
+    out = block.gather_buffer(world)
+    dist.all_gather_into_tensor(out.view(-1), block.buf, group=group)
+    return [block.views(out[r]) for r in range(world)]
 
 
 def unpack_blocks(parts):

@@ -1,8 +1,9 @@
 """The whole front end of one frame on the CPU through the oracle — TEST INFRASTRUCTURE ONLY
 (used by bench.py's cpu_baseline / --impl reference legs and by the end-to-end parity test).
 
-S1/S2 run the NumPy restatement of the reference's own NumPy code (or, where the read-only
-checkout exists and use_reference=True, that code itself through oracle/ref_shim.py); S3/S4/S5
+S1/S2 run the NumPy restatement of the reference's own NumPy code or, with use_reference=True
+(where the read-only checkout or its staged copy oracle/_ref/py exists), that code ITSELF through
+oracle/ref_shim.py; S3/S4/S5
 run the C restatement (oracle/c_oracle.c). Same stage order and inputs as
 dodt_b200.frontend.FrontEnd.enqueue.
 """
@@ -20,8 +21,36 @@ anchors = s.anchor_set
 frame_inputs = s.frame_inputs
 
 
+def reference_s1_s2_available():
+    """True when the reference's own S1/S2 Python can be imported (checkout or oracle/_ref/py)."""
+    from . import ref_shim
+    return ref_shim.available()
+
+
+_REF_GEN = None
+
+
+def _reference_s1_s2(pc, a):
+    """S1 + S2 by the reference's OWN code: BevSlices.generate_bev (bev_slices.py:33-150),
+    create_sliced_voxel_grid_2d (kitti_utils.py:212-277) and get_empty_anchor_filter_2d
+    (anchor_filter.py:64-119), imported through oracle/ref_shim.py."""
+    global _REF_GEN
+    from . import ref_shim
+    if _REF_GEN is None:
+        _REF_GEN = ref_shim.reference_bev_slices(s.HEIGHT_LO, s.HEIGHT_HI, s.NUM_SLICES)
+    from avod.core import anchor_filter
+    t0 = time.perf_counter()
+    bev = _REF_GEN.generate_bev("lidar", pc, s.GROUND_PLANE, np.asarray(s.AREA_EXTENTS), s.VOXEL_SIZE)
+    t1 = time.perf_counter()
+    vg = ref_shim.reference_sliced_voxel_grid_2d(pc, s.GROUND_PLANE, np.asarray(s.AREA_EXTENTS), s.VOXEL_SIZE)
+    keep = anchor_filter.get_empty_anchor_filter_2d(a, vg, 1)
+    t2 = time.perf_counter()
+    occ = (np.squeeze(vg.leaf_layout_2d) + 1).astype(np.uint8)
+    return bev, occ, keep, t1 - t0, t2 - t1
+
+
 def run_frame(inp, prev_bev_feat, rpn_nms=(1024, 0.8), avod_nms=(100, 0.01), timings=None,
-              k_boxes=None, prop_img_boxes=None, anchor_img_boxes=None):
+              k_boxes=None, prop_img_boxes=None, anchor_img_boxes=None, use_reference=False):
     """All stages of one frame; returns the outputs FrontEnd produces (for parity).
 
     The RPN decode (offset_to_anchor + projections) is the reference's NumPy chain, precomputed in
@@ -35,16 +64,19 @@ def run_frame(inp, prev_bev_feat, rpn_nms=(1024, 0.8), avod_nms=(100, 0.01), tim
     def tic():
         return time.perf_counter()
 
-    t0 = tic()
     pc = inp["points"].astype(np.float64)
-    bev = O.bev_slices(pc, s.GROUND_PLANE, s.AREA_EXTENTS, s.VOXEL_SIZE, s.HEIGHT_LO, s.HEIGHT_HI,
-                       s.NUM_SLICES)
-    t["S1"] = tic() - t0
-    t0 = tic()
-    occ, vox = O.occupancy_grid(pc, s.GROUND_PLANE, s.AREA_EXTENTS, s.VOXEL_SIZE)
-    keep = O.empty_anchor_filter_2d(a, occ, s.VOXEL_SIZE, vox["min_coord"][[0, 2]], 1)
+    if use_reference:
+        bev, occ, keep, t["S1"], t["S2"] = _reference_s1_s2(pc, a)
+    else:
+        t0 = tic()
+        bev = O.bev_slices(pc, s.GROUND_PLANE, s.AREA_EXTENTS, s.VOXEL_SIZE, s.HEIGHT_LO, s.HEIGHT_HI,
+                           s.NUM_SLICES)
+        t["S1"] = tic() - t0
+        t0 = tic()
+        occ, vox = O.occupancy_grid(pc, s.GROUND_PLANE, s.AREA_EXTENTS, s.VOXEL_SIZE)
+        keep = O.empty_anchor_filter_2d(a, occ, s.VOXEL_SIZE, vox["min_coord"][[0, 2]], 1)
+        t["S2"] = tic() - t0
     kept = np.flatnonzero(keep)
-    t["S2"] = tic() - t0
     t0 = tic()
     zeros = np.zeros(len(kept), dtype=np.int32)
     rpn_bev_crops = CO.crop_and_resize(inp["bev_1ch"], a_bev[kept], zeros, (3, 3))
@@ -86,7 +118,8 @@ def run_frame(inp, prev_bev_feat, rpn_nms=(1024, 0.8), avod_nms=(100, 0.01), tim
 def _worker(args):
     """One frame in one process. BLAS is held to one thread per process: the pool already uses
     every core, and np.dot inside get_point_filter would otherwise oversubscribe them."""
-    config, frame = args
+    config, frame = args[0], args[1]
+    use_reference = bool(args[2]) if len(args) > 2 else False
     try:
         from threadpoolctl import threadpool_limits
         threadpool_limits(1)
@@ -96,6 +129,6 @@ def _worker(args):
     prev, _ = s.feature_pair(config, frame + 1)
     t0 = time.perf_counter()
     timings = {}
-    out = run_frame(inp, prev, timings=timings)
+    out = run_frame(inp, prev, timings=timings, use_reference=use_reference)
     dt = time.perf_counter() - t0
     return dt, timings, int(len(out["top"])), int(len(out["final"]))
