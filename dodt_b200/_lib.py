@@ -117,6 +117,17 @@ SIGNATURES = {
 }
 
 _lib = None
+_path = LIB_PATH
+
+
+def use_diag_library():
+    """tools/ only: load libdodt_fe_diag.so (python -m dodt_b200._build --diag), the variant whose
+    measurement knobs read the environment. Must be called before the first load(); the package
+    itself never calls it, and no environment variable selects it."""
+    global _path
+    if _lib is not None:
+        raise RuntimeError("use_diag_library() must come before the library is first used")
+    _path = os.path.join(os.path.dirname(LIB_PATH), "libdodt_fe_diag.so")
 
 
 def load():
@@ -124,11 +135,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(_path):
         raise RuntimeError(
-            "libdodt_fe.so is not built (%s). Run `python -m dodt_b200._build` (needs nvcc); "
-            "this package has no CPU fallback." % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+            "%s is not built. Run `python -m dodt_b200._build` (needs nvcc); "
+            "this package has no CPU fallback." % _path)
+    lib = ctypes.CDLL(_path)
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError if the library lacks a declared symbol
         fn.restype = restype

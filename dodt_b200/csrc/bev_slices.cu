@@ -463,10 +463,8 @@ int dodt_bev_slices(const void *pts, int32_t pts_dtype, int64_t n, const int32_t
   // pipeline more)
   static int clear_blocks = -1, resolve_blocks_env = -1;
   if (clear_blocks < 0) {
-    const char *e = getenv("DODT_BEV_CLEAR_BLOCKS");
-    clear_blocks = e ? atoi(e) : 4 * kNumSMs;       // frame pipeline: 0 (driver memsets) 10.80, 296 10.98,
-    e = getenv("DODT_BEV_RESOLVE_BLOCKS");          // 592 11.03 k frames/s; resolve 1184 -> 592 CTAs: 11.07
-    resolve_blocks_env = e ? atoi(e) : 4 * kNumSMs;
+    clear_blocks = DODT_KNOB("DODT_BEV_CLEAR_BLOCKS", 4 * kNumSMs);   // frame pipeline: 0 (driver memsets) 10.80, 296 10.98,
+    resolve_blocks_env = DODT_KNOB("DODT_BEV_RESOLVE_BLOCKS", 4 * kNumSMs);   // 592 11.03 k frames/s; resolve 1184 -> 592 CTAs: 11.07
   }
   if (clear_blocks > 0 && reinterpret_cast<uintptr_t>(maps) % 16 == 0 && (!occ || reinterpret_cast<uintptr_t>(occ) % 16 == 0)) {
     bev_clear<<<clear_blocks, kBlock, 0, stream>>>(reinterpret_cast<uint4 *>(maps),

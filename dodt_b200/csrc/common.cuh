@@ -18,6 +18,23 @@ inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) 
 
 }  // namespace dodt
 
+// Measurement knobs. The PRODUCT library (libdodt_fe.so) is built without DODT_DIAG: every knob is
+// its compile-time default and no environment variable changes what a kernel computes or how it is
+// launched. tools/ build a separate libdodt_fe_diag.so (python -m dodt_b200._build --diag) in which
+// the knobs read the environment and the diagnostic kernel instantiations exist.
+#ifdef DODT_DIAG
+#include <stdlib.h>
+namespace dodt {
+inline int diag_knob(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+}  // namespace dodt
+#define DODT_KNOB(name, dflt) ::dodt::diag_knob(name, dflt)
+#else
+#define DODT_KNOB(name, dflt) (dflt)
+#endif
+
 #define DODT_CUDA_TRY(expr)                       \
   do {                                            \
     cudaError_t _e = (expr);                      \

@@ -36,7 +36,22 @@ int correlation_stream_tma(const float *const *maps, int n_pairs, float *const *
                            int C, int r, int out_h, int out_w, int shift, int max_ctas,
                            cudaStream_t stream);
 
+// correlation_feed.cu: TMA-fed persistent kernel (16-channel chunks); returns 1 when it does not apply
+int correlation_feed(const float *a, const float *b, int N, int H, int W, int C, int r, int out_h,
+                     int out_w, int shift, float *out, int max_ctas, cudaStream_t stream);
+
+int correlation_stream_feed(const float *const *maps, int n_pairs, float *const *outs, int H, int W,
+                            int C, int r, int out_h, int out_w, int shift, int max_ctas,
+                            cudaStream_t stream);
+
 namespace {
+
+// diagnostic build only: DODT_CORR_FEED=0 routes around the TMA-fed kernel (A/B timing)
+inline bool use_feed() {
+  static int v = -1;
+  if (v < 0) v = DODT_KNOB("DODT_CORR_FEED", 1);
+  return v != 0;
+}
 
 struct CorrGeom {
   int batch, H, W, C;
@@ -297,6 +312,11 @@ int dodt_correlation_shared(const float *a, const float *b, int32_t batch, int32
   // The reference reads the padded temporaries without bounds checks, so parameters that make a
   // displaced patch leave the padded image (pad < max_displacement with large displacements) are
   // undefined there; here such taps are zero.
+  if (g.ks == 1 && g.s1 == 1 && g.s2 == 2 && aligned && use_feed()) {
+    const int done = correlation_feed(a, b, g.batch, g.H, g.W, g.C, g.r, g.out_h, g.out_w,
+                                      g.md - g.pad, out, max_ctas, stream);
+    if (done <= 0) return done;
+  }
   if (g.ks == 1 && g.s1 == 1 && g.s2 == 2 && aligned) {
     const int done = correlation_tma(a, b, g.batch, g.H, g.W, g.C, g.r, g.out_h, g.out_w,
                                      g.md - g.pad, out, max_ctas, stream);
@@ -340,8 +360,13 @@ int dodt_correlation_stream(const float *const *maps, int32_t n_maps, float *con
     // groups of up to DODT_CORR_STREAM_MAX_PAIRS pairs per launch; neighbouring groups share a map
     while (j < n_maps - 1) {
       const int n = n_maps - 1 - j < DODT_CORR_STREAM_MAX_PAIRS ? n_maps - 1 - j : DODT_CORR_STREAM_MAX_PAIRS;
-      const int done = correlation_stream_tma(maps + j, n, outs + j, g.H, g.W, g.C, g.r, g.out_h,
-                                              g.out_w, g.md - g.pad, max_ctas, stream);
+      int done = 1;
+      if (use_feed())
+        done = correlation_stream_feed(maps + j, n, outs + j, g.H, g.W, g.C, g.r, g.out_h, g.out_w,
+                                       g.md - g.pad, max_ctas, stream);
+      if (done > 0)
+        done = correlation_stream_tma(maps + j, n, outs + j, g.H, g.W, g.C, g.r, g.out_h,
+                                      g.out_w, g.md - g.pad, max_ctas, stream);
       if (done < 0) return done;
       if (done > 0) break;   // not applicable: pair by pair below
       j += n;

@@ -29,7 +29,6 @@
 // Algorithmic HBM bytes per launch: 2*H*W*C*4 read once + H*W*25*4 written once (199.36 MB at
 // 700x800x32); halo re-reads (1.74x of B) are served by the 126 MB L2.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -545,12 +544,9 @@ int launch(const float *a, const float *b, int N, int H, int W, int C, int out_h
   alignas(64) CUtensorMap map_a, map_b;
   if (!make_map(&map_a, a, N, H, W, C, Cfg::AW, kTH) || !make_map(&map_b, b, N, H, W, C, Cfg::BW, Cfg::BH))
     return 1;  // not applicable (driver without tensor maps): caller falls back
-  static bool attr_set = false;
-  if (!attr_set) {
-    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_tma_k1<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  // the attribute belongs to the (function, device) pair: set on every launch (cheap)
+  DODT_CUDA_TRY(cudaFuncSetAttribute(corr_tma_k1<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES));
   CorrTmaGeom g;
   g.batch = N; g.C = C; g.out_h = out_h; g.out_w = out_w; g.shift = shift;
   g.tiles_x = ceil_div(out_w, kTW);
@@ -571,12 +567,9 @@ int launch_async(const float *a, const float *b, int N, int H, int W, int C, int
   constexpr int kThr = kTW / (2 * PX) * 2 * TH;
   constexpr int smem_bytes = (NST - 1) * Cfg::STAGE1_OFF + Cfg::STAGE_BYTES + 64;
   static_assert(NST == 2 || Cfg::SPARE == 0, "the staging spare region is laid out for two stages");
-  static bool attr_set = false;
-  if (!attr_set) {
-    DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R, PX, FRONT, TH, CTAS, NST, DBG>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  // the attribute belongs to the (function, device) pair: set on every launch (cheap)
+  DODT_CUDA_TRY(cudaFuncSetAttribute(corr_async_k1<R, PX, FRONT, TH, CTAS, NST, DBG>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   CorrAsyncGeom g;
   g.batch = N; g.H = H; g.W = W; g.C = C; g.out_h = out_h; g.out_w = out_w; g.shift = shift;
   g.tiles_x = ceil_div(out_w, kTW);
@@ -608,49 +601,26 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
   if (C % kCC != 0 || reinterpret_cast<uintptr_t>(a) % 16 || reinterpret_cast<uintptr_t>(b) % 16)
     return 1;
   if (static_cast<long long>(out_h) * out_w < 1024) return 1;  // tiny maps: tiles mostly padding
+#ifdef DODT_DIAG
+  // A/B instantiations and diagnostic builds (parts of the kernel compiled out: results INVALID for
+  // DBG 1/2/4/5/6) exist in libdodt_fe_diag.so only; the product library has neither the
+  // instantiations nor any environment lookup.
   static int impl = -1;
-  if (impl < 0) {
-    const char *e = getenv("DODT_CORR_IMPL");
-    impl = (e && e[0] == 't') ? 1 : ((e && e[0] == '2') ? 2 : ((e && e[0] == 'f') ? 3 : ((e && e[0] == '1') ? 4 : ((e && e[0] == '3') ? 6 : 0))));
-  }
-  if (impl == 1) {
+  if (impl < 0) impl = DODT_KNOB("DODT_CORR_IMPL", 0);
+  if (impl == 1) {   // tensor-TMA pipeline with 32-byte box rows
     switch (r) {
       case 1: return launch<1>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
       case 2: return launch<2>(a, b, N, H, W, C, out_h, out_w, shift, out, stream);
       default: return 1;
     }
   }
-  if (impl == 2) {   // 16 warps x 2 pixels per thread
-    switch (r) {
-      case 1: return launch_async<1, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
-      case 2: return launch_async<2, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
-      default: return 1;
-    }
-  }
-  if (impl == 3) {   // next unit's copies issued in the first half of the unit (A/B timing: slower)
-    switch (r) {
-      case 1: return launch_async<1, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
-      case 2: return launch_async<2, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
-      default: return 1;
-    }
-  }
-  if (impl == 6) {   // three-stage ring, 8-row tiles, one CTA per SM
-    switch (r) {
-      case 1: return launch_async<1, 4, 0, 8, 1, 3>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
-      case 2: return launch_async<2, 4, 0, 8, 1, 3>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
-      default: return 1;
-    }
-  }
-  if (impl == 4) {   // 16-row tiles, 8 warps, one CTA per SM (A/B timing: 68 us vs 59 us)
-    switch (r) {
-      case 1: return launch_async<1, 4, 0>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
-      case 2: return launch_async<2, 4, 0>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
-      default: return 1;
-    }
-  }
+  if (impl == 2 && r == 2) return launch_async<2, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+  if (impl == 3 && r == 2) return launch_async<2, 4, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+  if (impl == 6 && r == 2) return launch_async<2, 4, 0, 8, 1, 3>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
+  if (impl == 4 && r == 2) return launch_async<2, 4, 0>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
   {
     static int dbg = -1;
-    if (dbg < 0) { const char *e = getenv("DODT_CORR_DBG"); dbg = e ? atoi(e) : 0; }
+    if (dbg < 0) dbg = DODT_KNOB("DODT_CORR_DBG", 0);
     if (r == 2 && dbg == 1) return launch_async<2, 4, 0, 8, 2, 2, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
     if (r == 2 && dbg == 2) return launch_async<2, 4, 0, 8, 2, 2, 2>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
     if (r == 2 && dbg == 4) return launch_async<2, 4, 0, 8, 2, 2, 4>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
@@ -658,6 +628,7 @@ int correlation_tma(const float *a, const float *b, int N, int H, int W, int C, 
     if (r == 2 && dbg == 6) return launch_async<2, 4, 0, 8, 2, 2, 6>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
     if (r == 2 && dbg == 16) return launch_async<2, 4, 0, 8, 2, 2, 16>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream);
   }
+#endif
   // default: 8-row tiles, 4 warps per CTA, TWO CTAs per SM — the per-unit barrier, the exposed
   // tail of the copies and the epilogue of one CTA hide behind the other CTA's math
   switch (r) {
@@ -678,11 +649,13 @@ int correlation_stream_tma(const float *const *maps, int n_pairs, float *const *
   for (int k = 0; k <= n_pairs; ++k)
     if (reinterpret_cast<uintptr_t>(maps[k]) % 16) return 1;
   if (static_cast<long long>(out_h) * out_w < 1024) return 1;
+#ifdef DODT_DIAG
   static int dbg = -1;
-  if (dbg < 0) { const char *e = getenv("DODT_CORR_DBG"); dbg = e ? atoi(e) : 0; }
+  if (dbg < 0) dbg = DODT_KNOB("DODT_CORR_DBG", 0);
   if (r == 2 && dbg == 16)
     return launch_async<2, 4, 0, 8, 2, 2, 16>(nullptr, nullptr, n_pairs, H, W, C, out_h, out_w, shift, nullptr,
                                               max_ctas, stream, maps, outs);
+#endif
   switch (r) {
     case 1: return launch_async<1, 4, 0, 8, 2>(nullptr, nullptr, n_pairs, H, W, C, out_h, out_w, shift,
                                                nullptr, max_ctas, stream, maps, outs);

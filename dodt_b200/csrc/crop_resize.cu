@@ -268,8 +268,8 @@ bool plan_tables(CropMulti *m, int n_specs, int64_t n, unsigned *grid_x) {
     // ~4096 items (16 per thread) per CTA: measured in the frame pipeline, 512 / 1024 / 2048 / 4096 /
     // 8192 items give 10.50 / 10.62 / 10.70 / 10.88 / 10.80 k frames/s — fewer, longer CTAs cost the
     // co-running kernels less than many short ones, until too few CTAs are left to balance the SMs
-    static int target = -1;   // DODT_CROP_ITEMS overrides (experiments)
-    if (target < 0) { const char *e = getenv("DODT_CROP_ITEMS"); target = e ? atoi(e) : 16 * kCropThreads; }
+    static int target = -1;   // DODT_CROP_ITEMS overrides it in the diagnostic build only
+    if (target < 0) target = DODT_KNOB("DODT_CROP_ITEMS", 16 * kCropThreads);
     int R = static_cast<int>((target + per_roi - 1) / per_roi);
     if (R < 1) R = 1;
     if (R > kCropTableMax / axes) R = kCropTableMax / axes;

@@ -608,12 +608,9 @@ int dodt_nms(const float *boxes, const float *scores, int64_t n, const int32_t *
     DODT_CUDA_TRY(cudaMemsetAsync(ws + L.dead, 0, (L.state - L.dead) + sizeof(NmsState), stream));
 
   const size_t smem = static_cast<size_t>(kTriWords) * sizeof(unsigned long long);
-  static bool attr_set = false;  // per process; the attribute is a property of the function
-  if (!attr_set) {
-    DODT_CUDA_TRY(cudaFuncSetAttribute(nms_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    attr_set = true;
-  }
+  // the attribute belongs to the (function, device) pair: set on every launch (cheap)
+  DODT_CUDA_TRY(cudaFuncSetAttribute(nms_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
   const bool lazy = ni > kChunk;   // more than one chunk: order the candidates chunk by chunk
   int windows = 0;
   for (int chunk = first_window / kChunkWins; chunk * kChunk < ni; ++chunk) {
