@@ -355,15 +355,7 @@ def run_ours(args):
 
     stage_fns = {
         "S1_bev": lambda s, p: ops.bev_slices(s.points[:, :s.n_points], fe.bev_params, s.maps, s.occ, s.stats, s.ws_bev),
-        "S2_filter": lambda s, p: (ops.integral_image_2d(s.occ, s.ii, s.ws_ii),
-                                   ops.anchor_filter_2d(fe.anchors, s.ii, fe.nx, fe.nz, fe.min_x, fe.min_z,
-                                                        c.voxel_size, c.density_threshold, keep=s.keep),
-                                   ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact),
-                                   ops.gather_rows_multi([(fe.anchor_bev_boxes, s.k_bev_boxes),
-                                                          (fe.anchor_img_boxes, s.k_img_boxes),
-                                                          (s.rpn_scores, s.k_rpn_scores)], s.kept_idx, s.n_kept),
-                                   ops.rpn_decode(fe.anchors, s.rpn_offsets, s.kept_idx, s.n_kept, fe.bev_extents4,
-                                                  c.stereo_calib_p2, c.image_shape, s.k_rpn_boxes, None)),
+        "S2_filter": lambda s, p: fe.enqueue_s2(s),
         "S3_rpn_crops": lambda s, p: ops.crop_and_resize_multi([(s.bev_1ch, s.k_bev_boxes, s.rpn_bev_crops),
                                                                 (s.img_1ch, s.k_img_boxes, s.rpn_img_crops)],
                                                                c.rpn_crop, 0.0, n_dev=s.n_kept),

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(HERE, "libdodt_fe.so")
 DIAG_OBJ_DIR = os.path.join(HERE, "_obj_diag")
 DIAG_LIB_PATH = os.path.join(HERE, "libdodt_fe_diag.so")
 
-SOURCES = ["common.cu", "bev_slices.cu", "anchor_filter.cu", "crop_resize.cu", "correlation.cu", "correlation_tma.cu",
+SOURCES = ["common.cu", "bev_slices.cu", "anchor_filter.cu", "anchor_fused.cu", "crop_resize.cu", "correlation.cu", "correlation_tma.cu",
            "correlation_feed.cu", "correlation_grad.cu", "nms.cu", "frontend.cu", "anchors.cu", "lidar.cu"]
 
 NVCC_FLAGS = [

@@ -90,7 +90,8 @@ SIGNATURES = {
     "dodt_rpn_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double),
                                 POINTER(c_double), c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dodt_emit_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
+                                     c_void_p]),
     "dodt_crop_and_resize_multi": (c_int, [POINTER(CropSpec), c_int32, c_int32, c_void_p, c_int64,
                                            c_void_p, c_int32, c_int32, c_float, c_void_p]),
     "dodt_crop_and_resize": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
@@ -110,24 +111,35 @@ SIGNATURES = {
     "dodt_correlation_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                       c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                       c_void_p, c_size_t, c_void_p]),
+    "dodt_integral_banded_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "dodt_integral_band_rows": (c_int32, []),
+    "dodt_integral_image_2d_banded": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
+                                              POINTER(c_void_p), c_void_p]),
+    "dodt_anchor_filter_fused_workspace_bytes": (c_size_t, [c_int64]),
+    "dodt_anchor_filter_fused": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                         c_int32, c_int32, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dodt_nms_workspace_bytes": (c_size_t, [c_int64]),
     "dodt_nms_state_offset": (c_size_t, [c_int64]),
     "dodt_nms": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_float, c_int32, c_int32,
                          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
+DODT_FE_VERSION = 200   # include/dodt_fe.h
+
 _lib = None
-_path = LIB_PATH
+_diag = False
 
 
 def use_diag_library():
     """tools/ only: load libdodt_fe_diag.so (python -m dodt_b200._build --diag), the variant whose
     measurement knobs read the environment. Must be called before the first load(); the package
     itself never calls it, and no environment variable selects it."""
-    global _path
+    global _diag
     if _lib is not None:
         raise RuntimeError("use_diag_library() must come before the library is first used")
-    _path = os.path.join(os.path.dirname(LIB_PATH), "libdodt_fe_diag.so")
+    _diag = True
 
 
 def load():
@@ -135,6 +147,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    _path = os.path.join(os.path.dirname(LIB_PATH), "libdodt_fe_diag.so") if _diag else LIB_PATH
     if not os.path.exists(_path):
         raise RuntimeError(
             "%s is not built. Run `python -m dodt_b200._build` (needs nvcc); "
@@ -144,6 +157,10 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the library lacks a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes
+    got = lib.dodt_version()
+    if got != DODT_FE_VERSION:
+        raise RuntimeError("%s is version %d, this package expects %d: rebuild it (python -m dodt_b200._build)"
+                           % (_path, got, DODT_FE_VERSION))
     _lib = lib
     return lib
 

@@ -31,7 +31,8 @@ constexpr int kBandThreads = kBand * 32;
 
 __global__ void __launch_bounds__(kBandThreads)
 ii_band_scan(const unsigned char *__restrict__ occ, int nx, int nz, int vec_ok,
-             int *__restrict__ ii, int *__restrict__ bandsum) {
+             int *__restrict__ ii, int *__restrict__ bandsum, int *__restrict__ bandoff,
+             unsigned int *__restrict__ counter) {
   extern __shared__ unsigned short rowp[];  // [kBand][nz] inclusive row prefixes along z
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int band = blockIdx.x;
@@ -85,6 +86,33 @@ ii_band_scan(const unsigned char *__restrict__ occ, int nx, int nz, int vec_ok,
     }
     bandsum[static_cast<size_t>(band) * nz + z] = acc;
   }
+  if (!counter) return;
+  // Banded form (dodt_integral_image_2d_banded): the LAST band to finish turns the band totals
+  // into exclusive band offsets, so that no second launch is needed; consumers add
+  // bandoff[band of the row][z] to the band-local image themselves (anchor_fused.cu).
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int bands = gridDim.x;
+  for (int z = threadIdx.x; z < nz; z += kBandThreads) {
+    int run = 0;
+    for (int b0 = 0; b0 < bands; b0 += 16) {
+      int v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        v[k] = b0 + k < bands ? __ldcg(bandsum + static_cast<size_t>(b0 + k) * nz + z) : 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (b0 + k < bands) bandoff[static_cast<size_t>(b0 + k) * nz + z] = run;
+        run += v[k];
+      }
+    }
+  }
+  if (threadIdx.x == 0) *counter = 0u;   // re-armed for the next call on this workspace
 }
 
 // exclusive prefix of the band totals along the band axis: bandoff[b][z] = sum of bandsum[0..b-1][z].
@@ -211,7 +239,7 @@ int dodt_integral_image_2d(const uint8_t *occ, int32_t nx, int32_t nz, int32_t *
                                        static_cast<int>(smem)));
   const int vec_ok = (reinterpret_cast<uintptr_t>(occ) % 4 == 0 && nz % 4 == 0) ? 1 : 0;
   int *bandsum = static_cast<int *>(workspace);
-  ii_band_scan<<<bands, kBandThreads, smem, stream>>>(occ, nx, nz, vec_ok, ii, bandsum);
+  ii_band_scan<<<bands, kBandThreads, smem, stream>>>(occ, nx, nz, vec_ok, ii, bandsum, nullptr, nullptr);
   DODT_AFTER_LAUNCH();
   if (bands > 1) {
     int *bandoff = bandsum + static_cast<size_t>(bands) * nz;
@@ -221,6 +249,39 @@ int dodt_integral_image_2d(const uint8_t *occ, int32_t nx, int32_t nz, int32_t *
     ii_band_offsets<<<grid, 256, 0, stream>>>(nx, nz, ii, bandoff);
     DODT_AFTER_LAUNCH();
   }
+  return DODT_OK;
+}
+
+size_t dodt_integral_banded_workspace_bytes(int32_t nx, int32_t nz) {
+  if (nx <= 0 || nz <= 0) return 0;
+  return dodt_integral_workspace_bytes(nx, nz) + 256;   // + the finished-band counter
+}
+
+int32_t dodt_integral_band_rows(void) { return dodt::kBand; }
+
+int dodt_integral_image_2d_banded(const uint8_t *occ, int32_t nx, int32_t nz, int32_t *ii_local,
+                                  void *workspace, size_t workspace_bytes, int32_t **bandoff_out,
+                                  dodt_stream_t stream_) {
+  using namespace dodt;
+  if (!occ || !ii_local || nx <= 0 || nz <= 0) return DODT_EINVAL;
+  if (nz > 65535) return DODT_ECAPACITY;
+  const size_t need = dodt_integral_banded_workspace_bytes(nx, nz);
+  if (!workspace || workspace_bytes < need) return DODT_ECAPACITY;
+  if (reinterpret_cast<uintptr_t>(workspace) % 4 != 0) return DODT_EALIGN;
+  cudaStream_t stream = as_stream(stream_);
+  const int bands = ceil_div(nx, kBand);
+  const size_t smem = static_cast<size_t>(kBand) * nz * sizeof(unsigned short);
+  if (smem > 200 * 1024) return DODT_ECAPACITY;
+  if (smem > 48 * 1024)
+    DODT_CUDA_TRY(cudaFuncSetAttribute(ii_band_scan, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+  const int vec_ok = (reinterpret_cast<uintptr_t>(occ) % 4 == 0 && nz % 4 == 0) ? 1 : 0;
+  int *bandsum = static_cast<int *>(workspace);
+  int *bandoff = bandsum + static_cast<size_t>(bands) * nz;
+  unsigned int *counter = reinterpret_cast<unsigned int *>(bandoff + static_cast<size_t>(bands) * nz);
+  ii_band_scan<<<bands, kBandThreads, smem, stream>>>(occ, nx, nz, vec_ok, ii_local, bandsum, bandoff, counter);
+  DODT_AFTER_LAUNCH();
+  if (bandoff_out) *bandoff_out = bandoff;
   return DODT_OK;
 }
 

@@ -19,6 +19,7 @@
 // the float32 boxes they feed are identical except where a value sits on a float32 rounding edge.
 #include <math.h>
 
+#include "anchor_math.cuh"
 #include "common.cuh"
 
 namespace dodt {
@@ -150,21 +151,10 @@ rpn_decode_kernel(const double *__restrict__ anchors, const float *__restrict__ 
   const double *a = anchors + src * 6;
   const float *o = offsets + src * 6;
   double r[6];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    r[k] = __dadd_rn(__dmul_rn(static_cast<double>(__ldg(o + k)), __ldg(a + 3 + k)), __ldg(a + k));
-    r[3 + k] = exp(__dadd_rn(log(__ldg(a + 3 + k)), static_cast<double>(__ldg(o + 3 + k))));
-  }
+  decode_anchor(a, o, r);
   const double hx = __ddiv_rn(r[3], 2.0), hz = __ddiv_rn(r[5], 2.0);
-  if (bev_boxes) {   // [z1, x1, z2, x2] normalised (project_to_bev + reorder_projected_boxes)
-    const double xr = __dsub_rn(x_max, x_min), zr = __dsub_rn(z_max, z_min);
-    const double x1 = __ddiv_rn(__dsub_rn(__dsub_rn(r[0], hx), x_min), xr);
-    const double x2 = __ddiv_rn(__dsub_rn(__dadd_rn(r[0], hx), x_min), xr);
-    const double z1 = __ddiv_rn(__dsub_rn(__dsub_rn(z_max, __dadd_rn(r[2], hz)), z_min), zr);
-    const double z2 = __ddiv_rn(__dsub_rn(__dsub_rn(z_max, __dsub_rn(r[2], hz)), z_min), zr);
-    reinterpret_cast<float4 *>(bev_boxes)[i] = make_float4(__double2float_rn(z1), __double2float_rn(x1),
-                                                           __double2float_rn(z2), __double2float_rn(x2));
-  }
+  if (bev_boxes)   // [z1, x1, z2, x2] normalised (project_to_bev + reorder_projected_boxes)
+    reinterpret_cast<float4 *>(bev_boxes)[i] = bev_box_of(r, x_min, x_max, z_min, z_max);
   if (img_boxes) {   // [y1, x1, y2, x2] normalised (project_to_image_space + reorder)
     const double xs[2] = {__dadd_rn(r[0], hx), __dsub_rn(r[0], hx)};
     const double ys[2] = {r[1], __dsub_rn(r[1], r[4])};

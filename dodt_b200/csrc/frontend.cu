@@ -137,12 +137,20 @@ __global__ void __launch_bounds__(128)
 emit_detections(const float *__restrict__ boxes, const float *__restrict__ scores,
                 const int *__restrict__ keep, const int *__restrict__ n_keep, int max_det,
                 const int *__restrict__ frame_id, float *__restrict__ rows, int *__restrict__ counts,
-                int *__restrict__ frame_ids, int *__restrict__ cursor, int max_frames) {
+                int *__restrict__ frame_ids, int *__restrict__ cursor, int max_frames,
+                int *__restrict__ row_io, int rewrite) {
   __shared__ int s_row;
-  if (threadIdx.x == 0) s_row = atomicAdd(cursor, 1);
+  if (threadIdx.x == 0) {
+    if (rewrite) {
+      s_row = row_io[0];
+    } else {
+      s_row = atomicAdd(cursor, 1);
+      if (row_io) row_io[0] = s_row;
+    }
+  }
   __syncthreads();
   const int row = s_row;
-  if (row >= max_frames) return;
+  if (row < 0 || row >= max_frames) return;
   const int n = min(max_det, __ldg(n_keep));
   for (int k = threadIdx.x; k < max_det; k += 128) {
     float *dst = rows + (static_cast<size_t>(row) * max_det + k) * 6;
@@ -171,14 +179,15 @@ extern "C" {
 int dodt_emit_detections(const float *boxes, const float *scores, const int32_t *keep,
                          const int32_t *n_keep, int32_t max_det, const int32_t *frame_id,
                          float *rows, int32_t *counts, int32_t *frame_ids, int32_t *cursor,
-                         int32_t max_frames, dodt_stream_t stream_) {
+                         int32_t max_frames, int32_t *row_io, int32_t rewrite, dodt_stream_t stream_) {
   using namespace dodt;
   if (!boxes || !scores || !keep || !n_keep || !rows || !counts || !frame_ids || !cursor ||
-      max_det <= 0 || max_frames <= 0)
+      max_det <= 0 || max_frames <= 0 || (rewrite && !row_io))
     return DODT_EINVAL;
   if (reinterpret_cast<uintptr_t>(boxes) % 16 != 0) return DODT_EALIGN;
   emit_detections<<<1, 128, 0, as_stream(stream_)>>>(boxes, scores, keep, n_keep, max_det, frame_id,
-                                                     rows, counts, frame_ids, cursor, max_frames);
+                                                     rows, counts, frame_ids, cursor, max_frames, row_io,
+                                                     rewrite);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }

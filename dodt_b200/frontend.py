@@ -51,7 +51,10 @@ class FrontEndConfig:
     corr_max_displacement: int = 5
     corr_padding: int = 5
     corr_stride_2: int = 2
-    nms_max_windows: int = 4                        # launches reserved for the RPN NMS in a graph
+    nms_max_windows: int = 2                        # windows (1536 candidates each, a multiple of 2) reserved
+                                                    # for the RPN NMS in a graph; a frame that needs more
+                                                    # reports n_top[1] == 0 and is finished by
+                                                    # FrontEnd.complete_frame
     corr_max_ctas: int = 0                          # CTA cap of the correlation launch (0 = none: two
                                                     # persistent CTAs per SM). 148 (one per SM, the other
                                                     # half of each SM left to neighbouring frames) is ~2 %
@@ -112,6 +115,7 @@ class FrameSlot:
         r = _views(self.result_buf, fe.result_layout)
         self.n_kept, self.n_top, self.n_final = r["n_kept"], r["n_top"], r["n_final"]
         self.stats, self.top_idx, self.final_idx = r["stats"], r["top_idx"], r["final_idx"]
+        self.det_row = r["det_row"]            # row of the shard's DetectionBlock this frame wrote
         # ---- intermediates
         self.maps = e(c.num_slices + 1, H, W)
         self.occ = e(fe.nx, fe.nz, dtype=torch.uint8)
@@ -133,8 +137,10 @@ class FrameSlot:
         # ---- workspaces
         u8 = lambda n: torch.empty(max(int(n), 256), dtype=torch.uint8, device=dev)
         self.ws_bev = u8(ops.bev_workspace_bytes(c.max_points, c.num_slices, fe.nx, fe.nz))
-        self.ws_ii = u8(ops.integral_workspace_bytes(fe.nx, fe.nz))
-        self.ws_compact = u8(ops.load().dodt_compact_workspace_bytes(nA))
+        # zero before first use; the banded integral image and the fused filter leave them zero
+        self.ws_ii = torch.zeros(max(ops.integral_banded_workspace_bytes(fe.nx, fe.nz), 256),
+                                 dtype=torch.uint8, device=dev)
+        self.ws_fused = ops.anchor_filter_fused_workspace(nA, dev)
         self.ws_nms_rpn = u8(ops.nms_workspace_bytes(nA))
         self.ws_nms_final = u8(ops.nms_workspace_bytes(c.rpn_nms_size))
 
@@ -238,6 +244,7 @@ class FrontEnd:
             ("final_scores", (c.rpn_nms_size,), f32), ("frame_id", (2,), i32)])
         self.result_layout, self.result_bytes = _layout([
             ("n_kept", (1,), i32), ("n_top", (2,), i32), ("n_final", (2,), i32),
+            ("det_row", (1,), i32),
             ("stats", (BEV_STATS_LEN,), i32), ("top_idx", (c.rpn_nms_size,), i32),
             ("final_idx", (c.avod_nms_size,), i32)])
 
@@ -292,22 +299,66 @@ class FrontEnd:
             main.wait_stream(st)
         return ops.launch_count() - before
 
+    def _enqueue_proposals(self, s):
+        """What follows the RPN NMS: proposal boxes on the BEV map and (decoded again, eight fp64
+        corner projections each) on the image, for the survivors only."""
+        c = self.cfg
+        # one launch: the BEV boxes come out of the same arithmetic as k_rpn_boxes (same bits as a
+        # gather of the survivors' rows)
+        ops.rpn_decode(self.anchors, s.rpn_offsets, s.kept_idx, s.n_top, self.bev_extents4,
+                       c.stereo_calib_p2, c.image_shape, s.prop_bev_boxes, s.prop_img_boxes, idx2=s.top_idx)
+
+    # ---------------------------------------------------------------------------------------
+    def rpn_nms_complete(self, frame):
+        """True if the RPN NMS of the frame finished inside the windows the graph reserves
+        (FrontEndConfig.nms_max_windows). frame: a FrameSlot (reads 8 bytes from the device,
+        synchronising the current stream) or a HostFrame whose results were downloaded."""
+        if isinstance(frame, HostFrame):
+            return int(frame.results["n_top"][1]) == 1
+        return int(frame.n_top.cpu()[1]) == 1
+
+    def complete_frame(self, slot, block=None):
+        """Finish a frame whose RPN NMS did not complete inside the reserved windows: clustered
+        detections at IoU 0.8 can leave fewer than rpn_nms_size survivors among the top
+        nms_max_windows * 1536 candidates, and tf.image.non_max_suppression always scans on
+        (dt_rpn_model.py:587-591). Resumes the selection where the graph left it (same workspace,
+        first_window), then redoes everything downstream of it — proposal boxes, the 7x7 crops, the
+        final NMS — and REPLACES the frame's row of the detection block. Eager, on the current
+        stream, after the frame's graph has finished; the correlation map of the slot must still be
+        the frame's. Returns True if work was done."""
+        c = self.cfg
+        if self.rpn_nms_complete(slot):
+            return False
+        ops.nms(slot.k_rpn_boxes, slot.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=slot.top_idx,
+                n_keep=slot.n_top, workspace=slot.ws_nms_rpn, n_dev=slot.n_kept,
+                first_window=c.nms_max_windows, max_windows=0)
+        self._enqueue_proposals(slot)
+        self._enqueue_post(slot, block, (), rewrite=block is not None)
+        return True
+
+    def enqueue_s2(self, s):
+        """S2 of one slot (needs its occupancy grid from S1)."""
+        c = self.cfg
+        # two launches: the band-local integral image (+ band offsets by its last CTA), then
+        # filter + ordered compaction + crop boxes / scores of the kept anchors + the RPN decode
+        # of the kept anchors (dt_rpn_model.py:573-591: regressed anchors projected into the BEV
+        # map) in one kernel
+        bandoff, band_rows = ops.integral_image_2d_banded(s.occ, s.ii, s.ws_ii)
+        ops.anchor_filter_fused(self.anchors, s.ii, self.nx, self.nz, self.min_x, self.min_z,
+                                c.voxel_size, c.density_threshold, s.keep, s.kept_idx, s.n_kept,
+                                s.ws_fused, bandoff=bandoff, band_rows=band_rows,
+                                anchor_bev_boxes=self.anchor_bev_boxes, k_bev_boxes=s.k_bev_boxes,
+                                anchor_img_boxes=self.anchor_img_boxes, k_img_boxes=s.k_img_boxes,
+                                rpn_scores=s.rpn_scores, k_scores=s.k_rpn_scores,
+                                rpn_offsets=s.rpn_offsets, bev_extents=self.bev_extents4,
+                                k_rpn_boxes=s.k_rpn_boxes)
+
     def _enqueue_pre(self, s, skip):
         c = self.cfg
         if "S1" not in skip:
             ops.bev_slices(s.points[:, :s.n_points], self.bev_params, s.maps, s.occ, s.stats, s.ws_bev)
         if "S2" not in skip:
-            ops.integral_image_2d(s.occ, s.ii, s.ws_ii)
-            ops.anchor_filter_2d(self.anchors, s.ii, self.nx, self.nz, self.min_x, self.min_z,
-                                 c.voxel_size, c.density_threshold, keep=s.keep)
-            ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact)
-            ops.gather_rows_multi([(self.anchor_bev_boxes, s.k_bev_boxes),
-                                   (self.anchor_img_boxes, s.k_img_boxes),
-                                   (s.rpn_scores, s.k_rpn_scores)], s.kept_idx, s.n_kept)
-            # RPN decode of the kept anchors (dt_rpn_model.py:573-591,618-660): regressed anchors
-            # projected into the BEV map and the image
-            ops.rpn_decode(self.anchors, s.rpn_offsets, s.kept_idx, s.n_kept, self.bev_extents4,
-                           c.stereo_calib_p2, c.image_shape, s.k_rpn_boxes, None)
+            self.enqueue_s2(s)
         if "S3a" not in skip:
             ops.crop_and_resize_multi([(s.bev_1ch, s.k_bev_boxes, s.rpn_bev_crops),
                                        (s.img_1ch, s.k_img_boxes, s.rpn_img_crops)],
@@ -316,12 +367,9 @@ class FrontEnd:
             ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx,
                     n_keep=s.n_top, workspace=s.ws_nms_rpn, n_dev=s.n_kept,
                     max_windows=c.nms_max_windows)
-            ops.gather_rows_multi([(s.k_rpn_boxes, s.prop_bev_boxes)], s.top_idx, s.n_top)
-            # image boxes only for the proposals that survived (eight fp64 corner projections each)
-            ops.rpn_decode(self.anchors, s.rpn_offsets, s.kept_idx, s.n_top, self.bev_extents4,
-                           c.stereo_calib_p2, c.image_shape, None, s.prop_img_boxes, idx2=s.top_idx)
+            self._enqueue_proposals(s)
 
-    def _enqueue_post(self, s, block, skip):
+    def _enqueue_post(self, s, block, skip, rewrite=False):
         c = self.cfg
         if "S3b" not in skip:
             ops.crop_and_resize_multi([(s.bev_feat, s.prop_bev_boxes, s.bev_rois),
@@ -333,7 +381,7 @@ class FrontEnd:
                     keep=s.final_idx, n_keep=s.n_final, workspace=s.ws_nms_final, n_dev=s.n_top)
         if block is not None:
             ops.emit_detections(s.prop_bev_boxes, s.final_scores, s.final_idx, s.n_final, block,
-                                frame_id=s.frame_id)
+                                frame_id=s.frame_id, row_io=s.det_row, rewrite=rewrite)
 
     def capture(self, slot, prev_slot, block=None, skip=()):
         """Warm up eagerly once (sets kernel attributes), then capture `enqueue` into a graph.

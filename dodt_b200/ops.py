@@ -163,6 +163,57 @@ def anchor_filter_2d(anchors, ii, nx, nz, min_x, min_z, voxel_size, density_thre
     return keep
 
 
+def integral_banded_workspace_bytes(nx, nz):
+    return int(load().dodt_integral_banded_workspace_bytes(int(nx), int(nz)))
+
+
+def integral_image_2d_banded(occ, ii_local, workspace):
+    """occ [nx, nz] u8 -> band-local integral image ii_local [(nx+1), (nz+1)] i32 and, inside
+    `workspace` (zero before its first use), the exclusive band offsets: ONE launch. Returns the
+    band offsets as a tensor view [bands, nz] of the workspace and the rows per band; the full image
+    is ii_local[X, Z] + bandoff[(X-1) // band_rows, Z-1] (X, Z >= 1)."""
+    _need_cuda(occ, ii_local, workspace)
+    if occ.dim() != 2 or occ.dtype != torch.uint8 or not occ.is_contiguous():
+        raise TypeError("occupancy grid must be a contiguous 2-D uint8 tensor")
+    nx, nz = occ.shape
+    out = ctypes.c_void_p(0)
+    check(load().dodt_integral_image_2d_banded(_ptr(occ), nx, nz, _ptr(ii_local), _ptr(workspace),
+                                               workspace.numel(), ctypes.byref(out), _stream()),
+          "dodt_integral_image_2d_banded")
+    band_rows = int(load().dodt_integral_band_rows())
+    bands = (nx + band_rows - 1) // band_rows
+    off = out.value - workspace.data_ptr()
+    bandoff = workspace[off:off + bands * nz * 4].view(torch.int32).view(bands, nz)
+    return bandoff, band_rows
+
+
+def anchor_filter_fused_workspace(n, device):
+    """Zeroed workspace of anchor_filter_fused (every call leaves it zero again)."""
+    return torch.zeros(max(int(load().dodt_anchor_filter_fused_workspace_bytes(int(n))), 256),
+                       dtype=torch.uint8, device=device)
+
+
+def anchor_filter_fused(anchors, ii, nx, nz, min_x, min_z, voxel_size, density_threshold, keep, kept_idx,
+                        n_kept, workspace, bandoff=None, band_rows=0, anchor_bev_boxes=None, k_bev_boxes=None,
+                        anchor_img_boxes=None, k_img_boxes=None, rpn_scores=None, k_scores=None,
+                        rpn_offsets=None, bev_extents=None, k_rpn_boxes=None):
+    """S2 of the frame stream in one launch: keep mask of the float64 anchors, ordered compaction
+    (kept_idx, n_kept on the device) and, at the compacted positions, the anchors' crop boxes, RPN
+    scores and decoded BEV boxes. ii is the full integral image, or the band-local one when
+    bandoff / band_rows (integral_image_2d_banded) are given."""
+    _need_cuda(anchors, ii, bandoff, keep, kept_idx, n_kept, workspace, anchor_bev_boxes, k_bev_boxes,
+               anchor_img_boxes, k_img_boxes, rpn_scores, k_scores, rpn_offsets, k_rpn_boxes)
+    if anchors.dtype != torch.float64 or anchors.dim() != 2 or anchors.shape[1] != 6 or not anchors.is_contiguous():
+        raise TypeError("anchor_filter_fused expects contiguous float64 anchors (n, 6)")
+    n = anchors.shape[0]
+    check(load().dodt_anchor_filter_fused(
+        _ptr(anchors), n, _ptr(ii), _ptr(bandoff), int(band_rows), nx, nz, min_x, min_z, float(voxel_size),
+        float(density_threshold), _ptr(anchor_bev_boxes), _ptr(anchor_img_boxes), _ptr(rpn_scores),
+        _ptr(rpn_offsets), _dbl(bev_extents, 4) if bev_extents is not None else None, _ptr(keep),
+        _ptr(kept_idx), _ptr(n_kept), _ptr(k_bev_boxes), _ptr(k_img_boxes), _ptr(k_scores), _ptr(k_rpn_boxes),
+        _ptr(workspace), workspace.numel(), _stream()), "dodt_anchor_filter_fused")
+
+
 # ------------------------------------------------------------------------------------------ S3
 
 
@@ -331,17 +382,22 @@ def rpn_decode(anchors, offsets, idx, count, bev_extents, stereo_calib_p2, image
           "dodt_rpn_decode")
 
 
-def emit_detections(boxes, scores, keep, n_keep, block, frame_id=None):
+def emit_detections(boxes, scores, keep, n_keep, block, frame_id=None, row_io=None, rewrite=False):
     """Append keep[:n_keep[0]] of one frame to a dodt_b200.shard.DetectionBlock living on the device
-    (rows = box, score, index). frame_id: optional device int32 [2] (sequence, frame)."""
+    (rows = box, score, index). frame_id: optional device int32 [2] (sequence, frame). row_io:
+    optional device int32 [1] that receives the block row the frame was given; with rewrite=True
+    the list replaces row row_io[0] instead of taking a new one."""
     _need_cuda(boxes, scores, keep, n_keep, block.rows, block.counts, block.frame_ids, block.cursor,
-               frame_id)
+               frame_id, row_io)
+    if rewrite and row_io is None:
+        raise ValueError("rewrite needs row_io")
     max_frames, max_det = int(block.rows.shape[0]), int(block.rows.shape[1])
     if keep.numel() < max_det:
         raise ValueError("keep holds fewer than max_det entries")
     check(load().dodt_emit_detections(_ptr(boxes), _ptr(scores), _ptr(keep), _ptr(n_keep), max_det,
                                       _ptr(frame_id), _ptr(block.rows), _ptr(block.counts),
-                                      _ptr(block.frame_ids), _ptr(block.cursor), max_frames, _stream()),
+                                      _ptr(block.frame_ids), _ptr(block.cursor), max_frames, _ptr(row_io),
+                                      1 if rewrite else 0, _stream()),
           "dodt_emit_detections")
 
 

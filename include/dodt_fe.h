@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DODT_FE_VERSION 108 /* major*100 + minor */
+#define DODT_FE_VERSION 200 /* major*100 + minor */
 
 typedef void *dodt_stream_t; /* cudaStream_t */
 
@@ -131,6 +131,38 @@ size_t dodt_integral_workspace_bytes(int32_t nx, int32_t nz);
 /* ii: out int32 [(nx+1), (nz+1)], zero first row/column (integral_image_2d.py:30-37) */
 int dodt_integral_image_2d(const uint8_t *occ, int32_t nx, int32_t nz, int32_t *ii,
                            void *workspace, size_t workspace_bytes, dodt_stream_t stream);
+
+/* Banded form of the integral image for consumers that add the band offsets themselves (the fused
+ * kernel below): ONE launch writes the band-local image ii_local (zero row / column included) and,
+ * by the last band to finish, the exclusive band offsets; the full image of
+ * dodt_integral_image_2d is ii_local[X][Z] + bandoff[(X-1) / band_rows][Z-1] for X, Z >= 1.
+ * workspace: dodt_integral_banded_workspace_bytes, ZERO before its first use (the call leaves its
+ * counter zero); *bandoff_out (host pointer, optional) receives the device address of the offsets
+ * [ceil(nx / band_rows), nz] inside the workspace. */
+size_t dodt_integral_banded_workspace_bytes(int32_t nx, int32_t nz);
+int32_t dodt_integral_band_rows(void);
+int dodt_integral_image_2d_banded(const uint8_t *occ, int32_t nx, int32_t nz, int32_t *ii_local,
+                                  void *workspace, size_t workspace_bytes, int32_t **bandoff_out,
+                                  dodt_stream_t stream);
+
+/* S2 for the frame stream in one launch: the empty-anchor filter (avod/core/anchor_filter.py:64-119)
+ * on float64 anchors, the ordered compaction of the kept anchors (dt_rpn_model.py:952-958), the
+ * gather of their precomputed BEV / image crop boxes [n,4] and RPN scores [n], and the decoded,
+ * BEV-projected boxes of their regressed anchors (dt_rpn_model.py:573-591; same bits as
+ * dodt_rpn_decode). ii: the full integral image (bandoff NULL) or the band-local one with bandoff /
+ * band_rows from dodt_integral_image_2d_banded. Outputs: keep [n] u8, kept_idx [n] ascending,
+ * n_kept [1] (device), k_* [n,4] / [n] at the compacted positions (any of the k_* with its source
+ * may be NULL). workspace: dodt_anchor_filter_fused_workspace_bytes(n), ZERO before its first use
+ * (every call leaves it zero). Same results as dodt_anchor_filter_2d + dodt_compact_mask +
+ * dodt_gather_rows_multi + dodt_rpn_decode. */
+size_t dodt_anchor_filter_fused_workspace_bytes(int64_t n);
+int dodt_anchor_filter_fused(const double *anchors, int64_t n, const int32_t *ii, const int32_t *bandoff,
+                             int32_t band_rows, int32_t nx, int32_t nz, int32_t min_x, int32_t min_z,
+                             double voxel_size, double density_threshold, const float *anchor_bev_boxes,
+                             const float *anchor_img_boxes, const float *rpn_scores, const float *rpn_offsets,
+                             const double bev_extents[4], uint8_t *keep, int32_t *kept_idx, int32_t *n_kept,
+                             float *k_bev_boxes, float *k_img_boxes, float *k_scores, float *k_rpn_boxes,
+                             void *workspace, size_t workspace_bytes, dodt_stream_t stream);
 
 /* coords (n,2) [x,z] of dtype -> idx int32 (n,2); division in the coordinate dtype, truncation
  * toward zero, shift by the grid minimum, clip to [0, ndiv] (voxel_grid_2d.py:182-184) */
@@ -234,11 +266,14 @@ int dodt_rpn_decode(const double *anchors, const float *offsets, const int32_t *
  * rows [max_frames, max_det, 6] f32 = box (4), score, index into boxes; counts [max_frames];
  * frame_ids [max_frames, 2] = the two int32 at frame_id (sequence, frame; NULL: -2, row);
  * cursor: device int32, the next free row (incremented by the call; rows past max_frames are
- * dropped, the cursor keeps counting). All device pointers; graph-capturable. */
+ * dropped, the cursor keeps counting). row_io: optional device int32 — with rewrite == 0 the row the
+ * frame was given is stored there; with rewrite != 0 the frame's list REPLACES row *row_io (the
+ * cursor is untouched): how a frame whose RPN NMS had to be resumed corrects its entry.
+ * All device pointers; graph-capturable. */
 int dodt_emit_detections(const float *boxes, const float *scores, const int32_t *keep,
                          const int32_t *n_keep, int32_t max_det, const int32_t *frame_id,
                          float *rows, int32_t *counts, int32_t *frame_ids, int32_t *cursor,
-                         int32_t max_frames, dodt_stream_t stream);
+                         int32_t max_frames, int32_t *row_io, int32_t rewrite, dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * S3 — tf.image.crop_and_resize (TensorFlow 1.3.0 core/kernels/crop_and_resize_op.cc, bilinear),

@@ -178,3 +178,52 @@ def test_host_frame_and_detection_block(lib):
     assert int(block.cursor.item()) == 5
     ids = block.frame_ids.cpu().numpy()
     assert ids.tolist() == [[3, 51], [3, 52], [3, 52]]
+
+
+def test_frontend_resumes_incomplete_rpn_nms(lib):
+    """Clustered RPN outputs (many anchors regressed onto the same objects, the best scores among
+    them): at IoU 0.8 the 1024 proposals are NOT found inside the windows the frame graph reserves
+    for the RPN NMS, the graph reports n_top[1] == 0, and FrontEnd.complete_frame resumes the
+    selection and redoes what follows it. The reference always scans to completion
+    (tf.image.non_max_suppression, dt_rpn_model.py:587-591): the finished frame must equal the
+    oracle's, and its row of the detection block must have been replaced."""
+    from dodt_b200 import shard, synth
+    from dodt_b200.frontend import FrontEnd, HostFrame
+    fe = FrontEnd()
+    slots = [fe.new_slot(), fe.new_slot()]
+    inputs = [synth.frame_inputs(2, 60), synth.frame_inputs(2, 61)]
+    inputs[1].update(synth.clustered_rpn_outputs(2, 61, n_targets=60))
+    hosts = [HostFrame(fe).fill(inp, sequence=5, frame=60 + i) for i, inp in enumerate(inputs)]
+    for h, s in zip(hosts, slots):
+        h.upload(s)
+    block = shard.DetectionBlock(4, fe.cfg.avod_nms_size, fe.device)
+    graph, _ = fe.capture(slots[1], slots[0], block)
+    block.reset()
+    graph.replay()
+    hosts[1].download(slots[1])
+    torch.cuda.synchronize()
+    n_top, complete = slots[1].n_top.cpu().tolist()
+    assert complete == 0 and n_top < fe.cfg.rpn_nms_size, "the scene must not fit the reserved windows"
+    assert not fe.rpn_nms_complete(hosts[1]) and not fe.rpn_nms_complete(slots[1])
+    truncated = shard.gather_detections(block)[(5, 61)].clone()
+    assert fe.complete_frame(slots[1], block) is True
+    torch.cuda.synchronize()
+    assert fe.rpn_nms_complete(slots[1])
+    assert fe.complete_frame(slots[1], block) is False          # nothing left to do
+    ref = _reference_frame(fe, slots[1], inputs[1], inputs[0]["bev_feat"])
+    assert len(ref["top"]) == fe.cfg.rpn_nms_size
+    _check(slots[1], ref)
+    # the block still holds ONE row for the frame, now with the complete frame's detections
+    assert int(block.cursor.item()) == 1
+    got = shard.gather_detections(block)
+    assert list(got) == [(5, 61)]
+    rows = got[(5, 61)].numpy()
+    np.testing.assert_array_equal(rows[:, 5].astype(np.int64), ref["final"])
+    prop = slots[1].k_rpn_boxes[:len(ref["kept"])].cpu().numpy()[ref["top"]]
+    np.testing.assert_array_equal(rows[:, :4], prop[ref["final"]])
+    assert truncated.shape != rows.shape or not np.array_equal(truncated.numpy(), rows)
+    # an ordinary frame through the same graph afterwards is complete without help
+    hosts[1].fill(synth.frame_inputs(2, 62), sequence=5, frame=62).upload(slots[1])
+    graph.replay()
+    torch.cuda.synchronize()
+    assert fe.rpn_nms_complete(slots[1])

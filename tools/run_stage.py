@@ -39,9 +39,7 @@ for _ in range(reps):
     elif what == "bev":
         ops.bev_slices(s.points[:, :s.n_points], fe.bev_params, s.maps, s.occ, s.stats, s.ws_bev)
     elif what == "filter":
-        ops.integral_image_2d(s.occ, s.ii, s.ws_ii)
-        ops.anchor_filter_2d(fe.anchors, s.ii, fe.nx, fe.nz, fe.min_x, fe.min_z, c.voxel_size, c.density_threshold, keep=s.keep)
-        ops.compact_mask(s.keep, s.kept_idx, s.n_kept, s.ws_compact)
+        fe.enqueue_s2(s)
     elif what == "nms":
         ops.nms(s.k_rpn_boxes, s.k_rpn_scores, c.rpn_nms_size, c.rpn_nms_iou, keep=s.top_idx, n_keep=s.n_top,
                 workspace=s.ws_nms_rpn, n_dev=s.n_kept, max_windows=c.nms_max_windows)
