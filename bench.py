@@ -40,6 +40,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=60, help="sweeps of the resident slots (32 frames each)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="car", choices=["car", "kitti", "dense", "sequences"],
+                    help="car: BASELINE.json configs[1] + the tau=1 correlation of configs[2] (the headline); "
+                         "kitti: the same pipeline on a cloud with a real KITTI frame's occupancy (~12 k kept "
+                         "anchors); dense: configs[4] (500 k points, 0.05 m BEV 1400x1600: S1 + S2); "
+                         "sequences: configs[3] (8 sequences of ~300 frames dealt by dodt_b200.shard.plan, "
+                         "sensor inputs uploaded per frame)")
     ap.add_argument("--slots", type=int, default=32)
     ap.add_argument("--group", type=int, default=8,
                     help="consecutive frames per CUDA graph: their correlations share one launch")
@@ -208,6 +214,246 @@ def ncu_traffic():
     return None
 
 
+SEQUENCE_LENGTHS = [297, 310, 288, 305, 300, 315, 292, 301]   # configs[3]: 8 KITTI-tracking-shaped sequences
+
+
+def run_sequences_region(args, fe, slots, hosts, graphs, streams, main, block_unused, G, n_groups, launches,
+                         world, rank, local, dev, barrier):
+    """BASELINE.json configs[3]: 8 sequences of ~300 frames dealt to the ranks by dodt_b200.shard.plan
+    (whole sequences while there are at least as many sequences as ranks, contiguous chunks with a
+    one-frame halo otherwise). Every frame's sensor-side inputs (points, head outputs, its
+    (sequence, frame) id: 4 MB) are uploaded from pinned host memory inside the timed region, as a
+    real stream would; the BEV / image feature maps are network outputs that stay on the device.
+    Frames go through the same group graphs as the headline run; a chunk's halo frame and the
+    padding of a sequence's last group carry the id (-1, -1) and are dropped by the unpacking."""
+    import torch
+    import torch.distributed as dist
+
+    from dodt_b200 import shard
+    lengths = SEQUENCE_LENGTHS
+    plan = shard.plan(lengths, world, rank)
+    # work list: groups of G consecutive frames of one plan item, ids (-1, -1) for halo / padding
+    groups = []
+    for seq, first, end, halo in plan.items:
+        ids = ([(-1, -1)] if halo is not None else []) + [(seq, f) for f in range(first, end)]
+        while len(ids) % G:
+            ids.append((-1, -1))
+        groups += [ids[k:k + G] for k in range(0, len(ids), G)]
+    n_frames = plan.n_frames
+    max_frames = max(shard.plan(lengths, world, r).n_frames + 2 * G * len(shard.plan(lengths, world, r).items)
+                     for r in range(world))
+    block = shard.DetectionBlock(max_frames, fe.cfg.avod_nms_size, dev)
+    block.gather_buffer(world)
+    # the group graphs were captured against the headline block: re-capture against this one
+    graphs = []
+    for g_ in range(n_groups):
+        gr, launches = fe.capture_group(slots[g_ * G:(g_ + 1) * G], slots[g_ * G - 1], block)
+        graphs.append(gr)
+    torch.cuda.synchronize()
+    up_done = [None] * n_groups     # host buffers of group g may be rewritten after this event
+    done_ev = [None] * n_groups
+    up_ev = [None] * n_groups
+
+    def run(work):
+        for st in streams:
+            st.wait_stream(main)
+        for k, ids in enumerate(work):
+            g_ = k % n_groups
+            st = streams[g_]
+            if up_done[g_] is not None:
+                up_done[g_].synchronize()          # the previous upload from these host buffers has left
+            for j, (seq, f) in zip(range(g_ * G, (g_ + 1) * G), ids):
+                hosts[j].sensor["frame_id"][0] = seq
+                hosts[j].sensor["frame_id"][1] = f
+            with torch.cuda.stream(st):
+                ev = done_ev[(g_ + 1) % n_groups]
+                if ev is not None:
+                    st.wait_event(ev)              # the next group's graph read this group's last slot
+                for j in range(g_ * G, (g_ + 1) * G):
+                    hosts[j].upload(slots[j], False)
+                up_done[g_] = torch.cuda.Event()
+                up_done[g_].record(st)
+                up_ev[g_] = up_done[g_]
+                ev = up_ev[(g_ - 1) % n_groups]
+                if ev is not None:
+                    st.wait_event(ev)
+                graphs[g_].replay()
+                done_ev[g_] = torch.cuda.Event()
+                done_ev[g_].record(st)
+                for j in range(g_ * G, (g_ + 1) * G):
+                    hosts[j].download(slots[j])
+        for st in streams:
+            main.wait_stream(st)
+
+    run(groups[:2 * n_groups])                     # warm-up
+    if world > 1:
+        shard.all_gather_blocks(block)
+    barrier()
+    block.reset()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(main)
+    run(groups)
+    gathered = shard.all_gather_blocks(block)
+    b.record(main)
+    barrier()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    got = shard.unpack_blocks(gathered)
+    total = sum(lengths)
+    ok = sorted(got) == [(s_, f) for s_ in range(len(lengths)) for f in range(lengths[s_])]
+    if rank == 0:
+        print(json.dumps({
+            "metric": "front-end frames/sec", "value": total / (ms / 1e3), "unit": "frames/s", "n_gpus": world,
+            "steps": 1, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (f64 binning/predicates, i32 counts)", "data": "synthetic",
+            "config": {"workload": "configs[3]: %d sequences of %s frames dealt by dodt_b200.shard.plan over %d "
+                                   "rank(s) (%s); per frame: " % (len(lengths), lengths, world,
+                                                                 "whole sequences round-robin" if len(lengths) >= world
+                                                                 else "contiguous chunks with a one-frame halo")
+                                   + WORKLOAD,
+                       "step": "the whole job: %d frames" % total,
+                       "frames_this_rank": n_frames, "groups_this_rank": len(groups), "frames_per_graph": G},
+            "all_frames_gathered_exactly_once": bool(ok), "frames_gathered": len(got),
+            "e2e": {"value": total / (ms / 1e3), "unit": "frames/s",
+                    "h2d_bytes_per_step": hosts[0].sensor_buf.numel() * len(groups) * G * world,
+                    "d2h_bytes_per_step": hosts[0].result_buf.numel() * len(groups) * G * world,
+                    "note": "sensor inputs uploaded and results downloaded per frame inside the timed region"},
+            "gpu_launches": launches * len(groups),
+        }))
+
+
+def run_dense(args):
+    """BASELINE.json configs[4]: dense 128-beam cloud (500 k points), 0.05 m BEV (1400 x 1600 x 6 maps),
+    S1 (binning atomics + resolve) and S2 (integral image + 89 600-anchor filter) only — the stress
+    test of the binning atomics and the integral-image filter. A step is one sweep of the resident
+    buffer sets."""
+    import torch
+
+    from dodt_b200 import ops, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the front end has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n_pts, voxel, S = 500000, synth.VOXEL_SIZE_DENSE, synth.NUM_SLICES
+    nx, _, nz, min_x, _, min_z = ops.bev_grid(synth.AREA_EXTENTS, voxel)
+    params = ops.make_bev_params(synth.GROUND_PLANE, synth.AREA_EXTENTS, voxel, synth.HEIGHT_LO, synth.HEIGHT_HI,
+                                 S, True, 0.2, 2.0)
+    anchors = ops.grid_anchors(synth.AREA_EXTENTS, [[3.514, 1.581, 1.511], [4.236, 1.653, 1.547]],
+                               synth.ANCHOR_STRIDE, synth.GROUND_PLANE, dev)
+    nA = anchors.shape[0]
+    n_sets = 8
+    sets = []
+    for k in range(n_sets):
+        pc = torch.from_numpy(synth.point_cloud(5, 1000 * rank + k, n_points=n_pts)).to(dev)
+        sets.append(dict(
+            pts=pc.contiguous(), maps=torch.empty(S + 1, nz, nx, device=dev),
+            occ=torch.empty(nx, nz, dtype=torch.uint8, device=dev), stats=torch.empty(24, dtype=torch.int32, device=dev),
+            ws=torch.empty(max(ops.bev_workspace_bytes(n_pts, S, nx, nz), 256), dtype=torch.uint8, device=dev),
+            ii=torch.empty(nx + 1, nz + 1, dtype=torch.int32, device=dev),
+            ws_ii=torch.zeros(max(ops.integral_banded_workspace_bytes(nx, nz), 256), dtype=torch.uint8, device=dev),
+            ws_f=ops.anchor_filter_fused_workspace(nA, dev),
+            keep=torch.empty(nA, dtype=torch.uint8, device=dev), kept=torch.empty(nA, dtype=torch.int32, device=dev),
+            n_kept=torch.zeros(1, dtype=torch.int32, device=dev)))
+
+    def s1(x):
+        ops.bev_slices(x["pts"], params, x["maps"], x["occ"], x["stats"], x["ws"])
+
+    def s2(x):
+        bandoff, rows = ops.integral_image_2d_banded(x["occ"], x["ii"], x["ws_ii"])
+        ops.anchor_filter_fused(anchors, x["ii"], nx, nz, min_x, min_z, voxel, 1, x["keep"], x["kept"], x["n_kept"],
+                                x["ws_f"], bandoff=bandoff, band_rows=rows)
+
+    def graphs_of(fn):
+        out = []
+        for x in sets:
+            fn(x)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn(x)
+            out.append(g)
+        return out
+    before = ops.launch_count()
+    s1(sets[0]); s2(sets[0])
+    launches = ops.launch_count() - before
+    g_all = graphs_of(lambda x: (s1(x), s2(x)))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    main = torch.cuda.current_stream()
+
+    def sweeps(graphs, n, use_streams=True):
+        for st in streams:
+            st.wait_stream(main)
+        for _ in range(n):
+            for k, g in enumerate(graphs):
+                with torch.cuda.stream(streams[k % 4] if use_streams else main):
+                    g.replay()
+        for st in streams:
+            main.wait_stream(st)
+
+    K, Wm = max(args.steps, 1), max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sweeps(g_all, Wm)
+    torch.cuda.synchronize()
+    t_wait = time.time()
+    while rank == 0 and not sampler.rows and time.time() - t_wait < 3.0:
+        sweeps(g_all, 20)
+        torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    a.record()
+    sweeps(g_all, K)
+    b.record()
+    torch.cuda.synchronize()
+    sampler.window = (w0, time.time())
+    ms = a.elapsed_time(b)
+    clocks = sampler.stop() if rank == 0 else None
+    fps = K * n_sets / (ms / 1e3)
+
+    def stage_us(fn):
+        gs = graphs_of(fn)
+        sweeps(gs, 2, False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sweeps(gs, 8, False)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / (8 * n_sets)
+    t1, t2 = stage_us(s1), stage_us(s2)
+    b1 = 16 * n_pts + 4 * (S + 1) * nx * nz
+    b2 = nx * nz + 4 * (nx + 1) * (nz + 1) + 65 * nA
+    peak, peak_src = measured_peak()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "front-end frames/sec", "value": fps * world, "unit": "frames/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms / K, "frames_per_step": n_sets, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 binning/predicates, i32 counts)",
+            "data": "synthetic",
+            "config": {"workload": "configs[4] dense 128-beam LiDAR: %d points, %.2f m BEV %dx%dx%d (S1) + integral "
+                                   "image and %d-anchor filter (S2)" % (n_pts, voxel, nz, nx, S + 1, nA),
+                       "step": "one sweep of %d resident buffer sets (%.0f MB of maps each, > 126 MB L2 together)"
+                               % (n_sets, 4 * (S + 1) * nx * nz / 1e6),
+                       "anchors_kept": int(sets[0]["n_kept"].item()), "occupied_cells": int(sets[0]["occ"].sum())},
+            "roofline": {"bound": "hbm", "kernel": "bev_clear + bev_accumulate + bev_resolve_scan (S1)",
+                         "achieved": b1 / t1 / 1e3, "peak": peak, "unit": "GB/s", "frac": b1 / t1 / 1e3 / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": b1, "launch_us": t1,
+                         "S2": {"kernel": "ii_band_scan + anchor_filter_fused", "algorithmic_bytes": b2, "us": t2,
+                                "achieved": b2 / t2 / 1e3, "frac": b2 / t2 / 1e3 / peak},
+                         "frame": {"algorithmic_bytes": b1 + b2, "achieved": (b1 + b2) * fps / 1e9,
+                                   "frac": (b1 + b2) * fps / 1e9 / peak}},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": launches * n_sets * K,
+            "launches_per_frame": launches, "clocks": clocks,
+        }))
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -238,8 +484,12 @@ def run_ours(args):
     n_groups = n_slots // G
     slots = [fe.new_slot() for _ in range(n_slots)]
     # one KITTI-tracking-shaped stream per GPU: rank r reads frames of "sequence" r
-    hosts = [HostFrame(fe).fill(synth.frame_inputs(CONFIG_ID, 1000 * rank + i), sequence=rank, frame=i)
-             for i in range(n_slots)]
+    def frame_input(i):
+        inp = synth.frame_inputs(CONFIG_ID, 1000 * rank + i)
+        if args.workload == "kitti":      # realistic occupancy: ~18.5 k points, ~12 k kept anchors
+            inp["points"] = synth.point_cloud_kitti(CONFIG_ID, 1000 * rank + i)
+        return inp
+    hosts = [HostFrame(fe).fill(frame_input(i), sequence=rank, frame=i) for i in range(n_slots)]
     # this shard's detection lists: one fixed-size row block per frame, gathered ONCE at the end
     K, Wm = max(args.steps, 1), max(args.warmup, 3)
     F = K * n_slots                            # frames of the timed region: K sweeps of the slots
@@ -282,6 +532,13 @@ def run_ours(args):
         for st in streams:
             main.wait_stream(st)
 
+    if args.workload == "sequences":
+        run_sequences_region(args, fe, slots, hosts, graphs, streams, main, block, G, n_groups, launches,
+                             world, rank, local, dev, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -310,6 +567,9 @@ def run_ours(args):
     sampler.window = (w0, time.time())
     ms = ev0.elapsed_time(ev1)
     frames_recorded = min(int(block.cursor.item()), block.rows.shape[0])
+    # every resident frame's RPN NMS must have completed inside the windows the graph reserves
+    # (otherwise the runner's FrontEnd.complete_frame would have had to finish it: not timed here)
+    incomplete = sum(0 if fe.rpn_nms_complete(s_) else 1 for s_ in slots)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -528,7 +788,8 @@ def run_ours(args):
             "frames_timed": F * world, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 binning/predicates, i32 counts)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD,
+            "config": {"workload": WORKLOAD if args.workload == "car" else
+                       WORKLOAD + " [--workload kitti: 18.5k-point cloud with a real KITTI frame's occupancy]",
                        "step": "one sweep of the %d resident frame slots = %d frames per GPU" % (n_slots, n_slots),
                        "points": n_points, "anchors": fe.num_anchors,
                        "anchors_kept": n_kept, "proposals": n_top,
@@ -543,6 +804,7 @@ def run_ours(args):
             "launches_per_frame": launches / G, "clocks": clocks,
             "group_latency_us_single_stream": group_latency_us, "frames_per_graph": G,
             "streams": n_groups,
+            "rpn_nms_incomplete_slots": incomplete,
             "gathered": {"ranks": len(gathered), "frames_per_rank": int(block.rows.shape[0]),
                          "bytes_per_rank": int(block.rows.numel() * 4 + block.counts.numel() * 4
                                                + block.frame_ids.numel() * 4),
@@ -557,5 +819,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "dense":
+        run_dense(a)
     else:
         run_ours(a)

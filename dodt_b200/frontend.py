@@ -20,8 +20,8 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
-from . import anchors as A
 from . import ops, synth
+from .constants import CAR_ANCHOR_SIZES, KITTI_P2
 from ._lib import BEV_STATS_LEN
 
 
@@ -33,14 +33,14 @@ class FrontEndConfig:
     height_lo: float = synth.HEIGHT_LO
     height_hi: float = synth.HEIGHT_HI
     num_slices: int = synth.NUM_SLICES
-    anchor_3d_sizes: list = field(default_factory=lambda: [list(v) for v in A.CAR_ANCHOR_SIZES])
+    anchor_3d_sizes: list = field(default_factory=lambda: [list(v) for v in CAR_ANCHOR_SIZES])
     anchor_stride: list = field(default_factory=lambda: list(synth.ANCHOR_STRIDE))
     occ_lo: float = 0.2
     occ_hi: float = 2.0
     density_threshold: int = 1
     max_points: int = 131072
     image_shape: tuple = synth.IMAGE_SHAPE          # (360, 1200)
-    stereo_calib_p2: list = field(default_factory=lambda: [float(v) for v in A.KITTI_P2.reshape(-1)])
+    stereo_calib_p2: list = field(default_factory=lambda: [float(v) for v in KITTI_P2.reshape(-1)])
     feat_channels: int = 32
     rpn_crop: tuple = (3, 3)                        # rpn_proposal_roi_crop_size
     rpn_nms_size: int = 1024                        # rpn_train_nms_size

@@ -1,10 +1,12 @@
-"""Seeded synthetic KITTI-shaped inputs for tests and bench.py; NumPy, host side.
+"""Seeded synthetic KITTI-shaped RAW inputs of the front end for bench.py and tests;
+NumPy, host side: point clouds, feature maps and network-head outputs — what a frame slot consumes.
+The host-decoded boxes the CPU oracle needs on top of these live in oracle/synth_ref.py.
 
 Everything is a pure function of (config, frame): rng = default_rng(1000 * config + frame).
 """
 import numpy as np
 
-from . import anchors as A
+from .constants import CAR_ANCHOR_SIZES
 
 GROUND_PLANE = [0, -1, 0, 1.65]                       # wavedata tracking_utils.py:239 (hard-coded)
 AREA_EXTENTS = [[-40, 40], [-5, 3], [0, 70]]          # kitti_utils_config.area_extents
@@ -47,12 +49,6 @@ def point_cloud(config, frame, n_points=120000):
     return np.stack([x, y, z]).astype(np.float32)
 
 
-def car_anchors(area_extents=AREA_EXTENTS, ground_plane=GROUND_PLANE):
-    """The 89 600-anchor Car grid in anchor form (N, 6) float64 (dt_rpn_model.py:913,950)."""
-    boxes = A.tile_anchors_3d(area_extents, A.CAR_ANCHOR_SIZES, ANCHOR_STRIDE, ground_plane)
-    return A.box_3d_to_anchor(boxes)
-
-
 def feature_pair(config, frame, shape=(1, 700, 800, 32)):
     """Post-ReLU-like NHWC float32 features of frame t and t+1 (t shifted by (2,-2) px + noise)."""
     rng = np.random.default_rng(1000 * config + frame + 500000)
@@ -68,73 +64,48 @@ def rpn_offsets(config, frame, n):
     return rng.normal(0.0, 0.1, (n, 6)).astype(np.float32)
 
 
-def rpn_proposals(config, frame, anchors_kept):
-    """Regressed anchors, their normalised BEV boxes [x1,z1,x2,z2] (what dt_rpn_model.py:573-591
-    hands to NMS) and tie-free scores."""
+def num_car_anchors(area_extents=AREA_EXTENTS):
+    """Anchors of the Car grid: x columns x z rows x sizes x 2 rotations (89 600 for the car config;
+    grid_anchor_3d_generator.py:61-85)."""
+    nx = len(np.arange(area_extents[0][0] + ANCHOR_STRIDE[0] / 2.0, area_extents[0][1], step=ANCHOR_STRIDE[0]))
+    nz = len(np.arange(area_extents[2][1] - ANCHOR_STRIDE[1] / 2.0, area_extents[2][0], step=-ANCHOR_STRIDE[1]))
+    return nx * nz * len(CAR_ANCHOR_SIZES) * 2
+
+
+def rpn_scores(config, frame, n):
+    """The RPN head's objectness for n anchors: tie-free float32 scores (same random stream as
+    rpn_offsets: the offsets are drawn first)."""
     rng = np.random.default_rng(1000 * config + frame + 700000)
-    n = len(anchors_kept)
-    offsets = rng.normal(0.0, 0.1, (n, 6)).astype(np.float32).astype(np.float64)   # == rpn_offsets
-    regressed = A.offset_to_anchor(anchors_kept, offsets)
-    _, bev_norm = A.project_to_bev(regressed, BEV_EXTENTS)
-    scores = rng.permutation(np.linspace(0.01, 0.99, n)).astype(np.float32)
-    return regressed, bev_norm.astype(np.float32), scores
-
-
-def crop_boxes(anchors, image_shape=IMAGE_SHAPE):
-    """Normalised [y1,x1,y2,x2] float32 boxes on the BEV map and on the image for a set of anchors
-    (dt_rpn_model.py:975-985)."""
-    _, bev_norm = A.project_to_bev(anchors, BEV_EXTENTS)
-    _, img_norm = A.project_to_image_space(anchors, A.KITTI_P2, image_shape)
-    return (A.reorder_projected_boxes(bev_norm).astype(np.float32),
-            A.reorder_projected_boxes(img_norm).astype(np.float32))
-
-
-_ANCHOR_CACHE = None
-
-
-def anchor_set():
-    """(anchors (N,6) f64, their BEV boxes, their image boxes — both [y1,x1,y2,x2] f32)."""
-    global _ANCHOR_CACHE
-    if _ANCHOR_CACHE is None:
-        a = car_anchors()
-        _, bev_norm = A.project_to_bev(a, BEV_EXTENTS)
-        _, img_norm = A.project_to_image_space(a, A.KITTI_P2, IMAGE_SHAPE)
-        _ANCHOR_CACHE = (a, A.reorder_projected_boxes(bev_norm).astype(np.float32),
-                         A.reorder_projected_boxes(img_norm).astype(np.float32))
-    return _ANCHOR_CACHE
+    rng.normal(0.0, 0.1, (n, 6))
+    return rng.permutation(np.linspace(0.01, 0.99, n)).astype(np.float32)
 
 
 def frame_inputs(config, frame, n_points=120000, rpn_nms_size=1024):
     """Host inputs of one frame slot (dodt_b200.frontend.FrameSlot): synthetic sensor data and
-    synthetic network-head outputs, a pure function of (config, frame). `rpn_offsets` is what the
-    slot consumes; `rpn_boxes` / `rpn_img_boxes` are the same offsets decoded and projected on the
-    host (the reference's NumPy chain), for the CPU oracle."""
-    a, _, _ = anchor_set()
+    synthetic network-head outputs, a pure function of (config, frame)."""
+    n = num_car_anchors()
     rng = np.random.default_rng(1000 * config + frame + 900000)
     bev_feat, _ = feature_pair(config, frame)                          # [1,700,800,32]
     img_feat = np.abs(rng.standard_normal((1,) + tuple(IMAGE_SHAPE) + (32,), dtype=np.float32))
-    regressed, bev_norm, scores = rpn_proposals(config, frame, a)
-    _, img_norm = A.project_to_image_space(regressed, A.KITTI_P2, IMAGE_SHAPE)
+    final_scores = rng.permutation(np.linspace(0.01, 0.99, rpn_nms_size)).astype(np.float32)
     return dict(
         points=point_cloud(config, frame, n_points),
         bev_feat=bev_feat, img_feat=img_feat,
         bev_1ch=np.ascontiguousarray(bev_feat[..., :1]) * np.float32(0.5),
         img_1ch=np.ascontiguousarray(img_feat[..., :1]) * np.float32(0.5),
-        rpn_offsets=rpn_offsets(config, frame, len(a)),
-        rpn_boxes=A.reorder_projected_boxes(bev_norm).astype(np.float32),
-        rpn_img_boxes=A.reorder_projected_boxes(img_norm).astype(np.float32),
-        rpn_scores=scores,
-        final_scores=rng.permutation(np.linspace(0.01, 0.99, rpn_nms_size)).astype(np.float32))
+        rpn_offsets=rpn_offsets(config, frame, n),
+        rpn_scores=rpn_scores(config, frame, n),
+        final_scores=final_scores)
 
 
-def clustered_rpn_outputs(config, frame, n_targets=40, per_target=300, jitter=0.01):
+def clustered_rpn_outputs(config, frame, anchors, n_targets=40, per_target=300, jitter=0.01):
     """RPN head outputs shaped like a trained network's: the `per_target` anchors nearest to each of
     `n_targets` objects regress onto (almost) the same box and carry the highest scores, so that at
     IoU 0.8 nearly all of the best n_targets * per_target candidates suppress one another and
     tf.image.non_max_suppression has to scan far down the score order to fill its 1024 outputs.
-    Returns the keys of frame_inputs() it replaces: rpn_offsets, rpn_scores, rpn_boxes,
-    rpn_img_boxes."""
-    a, _, _ = anchor_set()
+    anchors: (n, 6) float64 anchor grid. Returns the frame_inputs() keys it replaces:
+    rpn_offsets (inverse of anchor_encoder.offset_to_anchor towards the targets), rpn_scores."""
+    a = np.asarray(anchors)
     n = len(a)
     rng = np.random.default_rng(1000 * config + frame + 1100000)
     offsets = rng.normal(0.0, 0.1, (n, 6))
@@ -153,15 +124,44 @@ def clustered_rpn_outputs(config, frame, n_targets=40, per_target=300, jitter=0.
         o[:, 0:3] = (target[0:3] - a[near, 0:3]) / a[near, 3:6]
         o[:, 3:6] = np.log(target[3:6] / a[near, 3:6])
         offsets[near] = o + rng.normal(0.0, jitter, o.shape)
-    offsets = offsets.astype(np.float32)
     n_cl = int(clustered.sum())
     scores = np.empty(n, dtype=np.float64)
     lin = np.linspace(0.01, 0.99, n)
     scores[clustered] = rng.permutation(lin[n - n_cl:])       # the clustered anchors score highest
     scores[~clustered] = rng.permutation(lin[:n - n_cl])
-    regressed = A.offset_to_anchor(a, offsets.astype(np.float64))
-    _, bev_norm = A.project_to_bev(regressed, BEV_EXTENTS)
-    _, img_norm = A.project_to_image_space(regressed, A.KITTI_P2, IMAGE_SHAPE)
-    return dict(rpn_offsets=offsets, rpn_scores=scores.astype(np.float32),
-                rpn_boxes=A.reorder_projected_boxes(bev_norm).astype(np.float32),
-                rpn_img_boxes=A.reorder_projected_boxes(img_norm).astype(np.float32))
+    return dict(rpn_offsets=offsets.astype(np.float32), rpn_scores=scores.astype(np.float32))
+
+
+def point_cloud_kitti(config, frame, n_points=18500, n_objects=64):
+    """(3, n) float32 camera-frame points with the OCCUPANCY of a real KITTI tracking frame after
+    the camera-FOV crop (SURVEY 8(d) "realistic ranges": 16-20 k points, 1.7-3.3 k occupied cells in
+    the 0.2-2.0 m filter slice, up to ~100 points in a cell, 9-15 k of the 89 600 anchors kept):
+    ground returns on scan rings, and compact objects (cars, poles, walls, vegetation) that carry
+    the points above 0.2 m — unlike point_cloud(), whose evenly spread points keep 60 k anchors."""
+    rng = np.random.default_rng(1000 * config + frame + 1300000)
+    n_ground = int(0.58 * n_points)
+    n_obj = n_points - n_ground
+    # ground: 64 beams, elevation -24.8..+2 deg, sensor 1.73 m above the road
+    elev = np.deg2rad(np.linspace(-24.8, -1.2, 56))
+    ring_r = 1.73 / np.tan(-elev)
+    ring = rng.integers(0, len(ring_r), n_ground)
+    r = ring_r[ring] * (1.0 + rng.normal(0, 0.004, n_ground))
+    th = rng.uniform(-0.72, 0.72, n_ground)
+    gx, gz = r * np.sin(th), r * np.cos(th)
+    gh = rng.normal(0.0, 0.035, n_ground)
+    # objects: centres in the field of view, a footprint of a few square metres, points ~ 1/range
+    oz = rng.uniform(6, 68, n_objects)
+    ox = rng.uniform(-1, 1, n_objects) * np.minimum(38.0, oz * 0.8)
+    half = np.stack([rng.uniform(0.2, 1.6, n_objects), rng.uniform(0.1, 0.5, n_objects)], axis=1)
+    top = rng.uniform(0.8, 2.2, n_objects)
+    w = 1.0 / np.maximum(oz, 8.0) ** 1.5
+    which = rng.choice(n_objects, n_obj, p=w / w.sum())
+    px = ox[which] + rng.uniform(-1, 1, n_obj) * half[which, 0]
+    pz = oz[which] + rng.uniform(-1, 1, n_obj) * half[which, 1]
+    ph = rng.uniform(0.05, 1.0, n_obj) * top[which]
+    x = np.clip(np.concatenate([gx, px]), -39.99, 39.99)
+    z = np.clip(np.concatenate([gz, pz]), 0.01, 69.99)
+    h = np.concatenate([gh, ph])
+    order = rng.permutation(n_points)            # file order is not sorted by anything
+    y = 1.65 - h
+    return np.stack([x, y, z]).astype(np.float32)[:, order]

@@ -1,8 +1,9 @@
-"""Host-side (NumPy) anchor geometry that sits between the stages of the front end. These produce
-the INPUTS of the GPU stages (anchor grid for S2, normalised boxes for S3/S5); they mirror the
-reference helpers so that synthetic benchmarks and tests feed the kernels exactly what DODT does.
-They are small per-frame array maths, not part of the accelerated path (SURVEY §8(f) rank 1 lists
-moving them onto the device as the next widening step).
+"""Host-side (NumPy) mirror of the reference's anchor helpers — TEST INFRASTRUCTURE (oracle/).
+
+These restate the small per-frame array maths that sits between the stages of the front end in the
+reference; tests and the CPU baseline use them to produce what the reference's host code would feed
+the stages, and tests/test_oracle_vs_reference.py pins them to the live reference. The product
+computes the same things on the device (dodt_b200/csrc/anchors.cu) and never imports this module.
 
   tile_anchors_3d         avod/core/anchor_generators/grid_anchor_3d_generator.py:39-108
   box_3d_to_anchor        avod/core/box_3d_encoder.py:85-132
@@ -13,12 +14,7 @@ moving them onto the device as the next widening step).
 """
 import numpy as np
 
-# KITTI Car clusters of avod/configs/pyramid_cars_with_aug_dt_5_tracking.config (2 clusters)
-CAR_ANCHOR_SIZES = [[3.514, 1.581, 1.511], [4.236, 1.653, 1.547]]
-# P2 of avod/tests/datasets/Kitti/tracking/training/calib/0000.txt (public KITTI calibration)
-KITTI_P2 = np.array([[721.5377, 0.0, 609.5593, 44.85728],
-                     [0.0, 721.5377, 172.854, 0.2163791],
-                     [0.0, 0.0, 1.0, 0.002745884]])
+from dodt_b200.constants import CAR_ANCHOR_SIZES, KITTI_P2  # noqa: F401  (re-exported)
 
 
 def tile_anchors_3d(area_extents, anchor_3d_sizes, anchor_stride, ground_plane):

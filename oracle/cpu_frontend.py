@@ -11,8 +11,8 @@ import time
 
 import numpy as np
 
-from dodt_b200 import anchors as A
-from dodt_b200 import synth as s
+from . import anchor_helpers as A  # noqa: F401
+from . import synth_ref as s
 
 from . import c_oracle as CO
 from . import np_oracle as O

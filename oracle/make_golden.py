@@ -32,8 +32,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from dodt_b200 import anchors as A  # noqa: E402
-from dodt_b200 import synth as S  # noqa: E402
+from oracle import anchor_helpers as A  # noqa: E402
+from oracle import synth_ref as S  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")

@@ -62,7 +62,7 @@ def inputs(shape, kw, seed=0):
 
 def full_inputs():
     """Config C: the bench's synthetic BEV feature pair [1,700,800,32] and a seeded gradient."""
-    from dodt_b200 import synth
+    from oracle import synth_ref as synth
     f0, f1 = synth.feature_pair(3, 0)
     g = np.random.default_rng(11).standard_normal((1, 700, 800, 25)).astype(np.float32)
     return f0, f1, g

@@ -174,8 +174,9 @@ def test_grid_anchor_shape_matches_reference_arange(lib):
     """Host-only: (nz, nx, sizes, rotations) == the np.arange lengths of
     avod/core/anchor_generators/grid_anchor_3d_generator.py:62-72, including the degenerate areas
     of grid_anchor_3d_generator_test.py:32-70."""
-    from dodt_b200 import anchors as A
-    from dodt_b200 import ops, synth
+    from oracle import anchor_helpers as A
+    from dodt_b200 import ops
+    from oracle import synth_ref as synth
     assert ops.grid_anchor_shape(synth.AREA_EXTENTS, synth.ANCHOR_STRIDE, 2) == (140, 160, 2, 2)
     for ext, stride in (([(-1., 1.), (-1., 0.), (0., 1.)], [1, 1]), ([(0., 0.), (-1., 0.), (0., 2.)], [1, 1]),
                         ([(-1., 1.), (-1., 0.), (0., 0.)], [1, 1]), ([(-3.3, 7.1), (-1, 0), (0.2, 9.9)], [0.7, 0.3])):

@@ -146,7 +146,7 @@ def test_gpu_correlation_autograd_and_partial_grads(dd):
 def test_gpu_correlation_grad_full_size_properties(dd):
     """Config C size [1,700,800,32]: the oracle on border / interior strips, and the adjoint
     identity <gA, A> = <G, corr(A, B)> = <gB, B> over the whole map."""
-    from dodt_b200 import synth
+    from oracle import synth_ref as synth
     f0, f1 = synth.feature_pair(3, 0)
     kw = dict(kernel_size=1, max_displacement=5, stride_1=1, stride_2=2, padding=5)
     rng = np.random.default_rng(11)

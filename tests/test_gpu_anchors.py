@@ -1,12 +1,12 @@
-"""GPU parity of the device-side anchor geometry against dodt_b200.anchors —
+"""GPU parity of the device-side anchor geometry against oracle.anchor_helpers —
 the NumPy restatement of the reference helpers that tests/test_oracle_vs_reference.py pins to the
 LIVE reference — and against the answers the reference's unit tests assert."""
 import numpy as np
 import pytest
 import torch
 
-from dodt_b200 import anchors as A
-from dodt_b200 import synth as S
+from oracle import anchor_helpers as A
+from oracle import synth_ref as S
 
 pytestmark = pytest.mark.gpu
 

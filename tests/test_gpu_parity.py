@@ -23,7 +23,7 @@ def dd(lib):
 
 
 def _cfg():
-    from dodt_b200 import synth
+    from oracle import synth_ref as synth
     return synth
 
 
@@ -252,7 +252,7 @@ def test_anchor_filter_reference_3d_masks_in_2d(dd):
     pts = np.array([[0.51, -0.5, 1.1], [1.51, -0.5, 1.1]])
     vg = dd.VoxelGrid2D()
     vg.voxelize_2d(pts, 0.5, extents=[(0., 2.), (-1., 0.), (0., 2.)])
-    from dodt_b200.anchors import box_3d_to_anchor
+    from oracle.anchor_helpers import box_3d_to_anchor
     boxes = np.array([[0.51, 0, 0.51, 1, 1, 1, 0], [0.51, 0, 0.51, 1, 1, 1, np.pi / 2.],
                       [0.51, 0, 1.1, 1, 1, 1, 0], [0.51, 0, 1.1, 1, 1, 1, np.pi / 2.],
                       [1.51, 0, 0.51, 1, 1, 1, 0], [1.51, 0, 0.51, 1, 1, 1, np.pi / 2.],
@@ -487,7 +487,7 @@ def test_bev_and_filter_adversarial_random_configs(dd, seed):
     boundaries +- one ulp, to the open extents, duplicates, and points outside. S1 maps, winner
     indices, counts and occupancy must equal the oracle bit for bit; the S2 keep mask on random
     (partly out-of-range, partly negative) anchors likewise."""
-    from dodt_b200 import synth
+    from oracle import synth_ref as synth
     from adversarial import adversarial_case
     rng = np.random.default_rng(1900 + seed)
     pc, voxel, ext, lo, hi, S = adversarial_case(seed)

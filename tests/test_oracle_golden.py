@@ -17,8 +17,8 @@ import os
 import numpy as np
 import pytest
 
-from dodt_b200 import anchors as A
-from dodt_b200 import synth as S
+from oracle import anchor_helpers as A
+from oracle import synth_ref as S
 from oracle import c_oracle as CO
 from oracle import np_oracle as O
 

@@ -6,8 +6,8 @@ outputs under tests/golden/ (tests/test_oracle_golden.py) cover that case.
 import numpy as np
 import pytest
 
-from dodt_b200 import anchors as A
-from dodt_b200 import synth as S
+from oracle import anchor_helpers as A
+from oracle import synth_ref as S
 from oracle import np_oracle as O
 from oracle import ref_shim
 
@@ -108,7 +108,7 @@ def test_voxelize_2d_live():
 
 
 def test_anchor_helpers_live():
-    """dodt_b200.anchors (host-side inputs of S2/S3/S5) == the reference helpers."""
+    """oracle.anchor_helpers (host-side inputs of S2/S3/S5) == the reference helpers."""
     from avod.core import anchor_encoder, anchor_projector, box_3d_encoder
     from avod.core.anchor_generators import grid_anchor_3d_generator as G
     boxes = G.tile_anchors_3d(S.AREA_EXTENTS, A.CAR_ANCHOR_SIZES, S.ANCHOR_STRIDE, S.GROUND_PLANE)

@@ -195,7 +195,7 @@ def test_gpu_correlation_full_size_vs_live_reference_kernels(dd):
     frozen ones."""
     if not R.available():
         pytest.skip("oracle/_ref/libcorr_ref.so did not travel to this box")
-    from dodt_b200 import synth
+    from oracle import synth_ref as synth
     a, b = synth.feature_pair(7, 3)
     g = np.random.default_rng(77).standard_normal((1, 700, 800, 25)).astype(np.float32)
     want = R.correlation(a, b, **S.DODT)

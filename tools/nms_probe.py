@@ -2,7 +2,8 @@
 import os, sys, struct
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from dodt_b200 import ops, synth
+from dodt_b200 import ops
+    from oracle import synth_ref as synth
 from dodt_b200._lib import load
 anch = synth.car_anchors()
 rng = np.random.default_rng(0)

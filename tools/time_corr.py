@@ -3,7 +3,8 @@ usage: python tools/time_corr.py [max_ctas]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from dodt_b200 import ops, synth
+from dodt_b200 import ops
+    from oracle import synth_ref as synth
 torch.manual_seed(0)
 max_ctas = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 bufs = [(torch.rand(1, 700, 800, 32, device="cuda"), torch.rand(1, 700, 800, 32, device="cuda"),
