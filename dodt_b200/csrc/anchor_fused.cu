@@ -7,7 +7,7 @@
 //   avod/core/models/dt_rpn_model.py:975-985 BEV / image crop boxes of the kept anchors
 //   avod/core/models/dt_rpn_model.py:573-591 regressed anchors of the kept anchors -> BEV boxes
 //
-// A CTA owns a tile of 1024 consecutive anchors: box sums from the integral image (either the full
+// A CTA owns a tile of kFuseBlock consecutive anchors: box sums from the integral image (either the full
 // image or the band-local image + band offsets that dodt_integral_image_2d_banded leaves, which
 // saves the pass that adds the offsets), keep flags, block scan, decoupled look-back over the tile
 // aggregates for the global position (ordered, so kept_idx ascends like NumPy boolean indexing),
@@ -20,7 +20,7 @@
 namespace dodt {
 namespace {
 
-constexpr int kFuseBlock = 1024;
+constexpr int kFuseBlock = 256;
 
 __device__ __forceinline__ int trunc_index_f32(float v, float voxel) { return __float2int_rz(__fdiv_rn(v, voxel)); }
 __device__ __forceinline__ int clip_index(int trunc, int min_coord, int ndiv) {
@@ -93,14 +93,14 @@ anchor_filter_fused(const FusedArgs g) {
   if (lane == 0) s_warp[warp] = __popc(ballot);
   __syncthreads();
   if (warp == 0) {
-    const int v = s_warp[lane];
+    const int v = lane < kFuseBlock / 32 ? s_warp[lane] : 0;
     int w = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int up = __shfl_up_sync(0xffffffffu, w, d);
       if (lane >= d) w += up;
     }
-    s_warp[lane] = w - v;                       // exclusive
+    if (lane < kFuseBlock / 32) s_warp[lane] = w - v;   // exclusive
     if (lane == 31) s_total = w;
   }
   __syncthreads();
@@ -108,25 +108,34 @@ anchor_filter_fused(const FusedArgs g) {
   const int total = s_total;
   if (keep) s_list[local] = threadIdx.x;
 
-  // ---- decoupled look-back: exclusive prefix of the tile totals (one thread; tiles run in
-  // ticket order, so every predecessor has started)
-  if (threadIdx.x == 0) {
+  // ---- decoupled look-back: exclusive prefix of the tile totals. Warp 0 inspects 32 predecessors
+  // per step (tiles run in ticket order, so every predecessor has started): the chain of dependent
+  // L2 reads is tile/32 long instead of tile.
+  if (warp == 0) {
+    if (lane == 0 && tile > 0) atomicExch(g.status + tile, (1ull << 32) | static_cast<unsigned>(total));
     int base = 0;
-    if (tile > 0) {
-      atomicExch(g.status + tile, (1ull << 32) | static_cast<unsigned>(total));
-      for (int j = tile - 1; j >= 0; --j) {
-        unsigned long long st;
+    for (int j = tile - 1; j >= 0; j -= 32) {
+      const int idx = j - lane;
+      unsigned long long st = 2ull << 32;            // before the first tile: inclusive prefix 0
+      if (idx >= 0) {
         do {
-          st = *reinterpret_cast<volatile unsigned long long *>(g.status + j);
+          st = *reinterpret_cast<volatile unsigned long long *>(g.status + idx);
         } while ((st >> 32) == 0);
-        base += static_cast<int>(st & 0xffffffffu);
-        if ((st >> 32) == 2) break;
       }
+      const unsigned inclusive = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+      const int stop = inclusive ? __ffs(inclusive) - 1 : 31;   // nearest predecessor with a full prefix
+      int v = lane <= stop ? static_cast<int>(st & 0xffffffffu) : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      base += v;
+      if (inclusive) break;
     }
-    __threadfence();
-    atomicExch(g.status + tile, (2ull << 32) | static_cast<unsigned>(base + total));
-    s_base = base;
-    if (tile == n_tiles - 1) *g.n_kept = base + total;
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(g.status + tile, (2ull << 32) | static_cast<unsigned>(base + total));
+      s_base = base;
+      if (tile == n_tiles - 1) *g.n_kept = base + total;
+    }
   }
   __syncthreads();
   const int base = s_base;

@@ -358,7 +358,8 @@ bool feed_applies(int C, int out_h, int out_w, int H, int W) {
   return C % 16 == 0 && static_cast<long long>(out_h) * out_w >= 1024 && H >= 1 && W >= 1;
 }
 
-// diagnostic build: DODT_CORR_FEED = 1 -> 8-channel units, two stages; 2 -> 16-channel units, one stage
+// diagnostic build: DODT_CORR_FEED = 1 -> 8-channel units, two stages; 2 -> 16-channel units, one stage;
+// 3 / 4 -> 8-channel units, four / three stages (one CTA per SM)
 template <int R>
 int launch_variant(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w, int shift,
                    float *out, int max_ctas, cudaStream_t stream, const float *const *maps, float *const *outs) {
@@ -366,6 +367,8 @@ int launch_variant(const float *a, const float *b, int N, int H, int W, int C, i
   static int v = -1;
   if (v < 0) v = DODT_KNOB("DODT_CORR_FEED", 1);
   if (v == 2) return launch_feed<R, 16, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream, maps, outs);
+  if (v == 3) return launch_feed<R, 8, 4>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream, maps, outs);
+  if (v == 4) return launch_feed<R, 8, 3>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream, maps, outs);
 #endif
   return launch_feed<R, kFeedCH, kFeedNST>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream, maps, outs);
 }

@@ -14,9 +14,12 @@ import torch  # noqa: E402
 from dodt_b200 import ops  # noqa: E402
 
 pairs = [1, 4, 8]
+ctas = 0
 for i, a in enumerate(sys.argv):
     if a == "--pairs":
         pairs = [int(v) for v in sys.argv[i + 1].split(",")]
+    if a == "--ctas":
+        ctas = int(sys.argv[i + 1])
 torch.manual_seed(0)
 H, W, C = 700, 800, 32
 for k in pairs:
@@ -26,9 +29,9 @@ for k in pairs:
 
     def launch(i):
         if k == 1:
-            ops.correlation(maps[i][0], maps[i][1], 1, 5, 1, 2, 5, out=outs[i][0])
+            ops.correlation(maps[i][0], maps[i][1], 1, 5, 1, 2, 5, out=outs[i][0], max_ctas=ctas)
         else:
-            ops.correlation_stream(maps[i], 1, 5, 1, 2, 5, outs=outs[i])
+            ops.correlation_stream(maps[i], 1, 5, 1, 2, 5, outs=outs[i], max_ctas=ctas)
     for i in range(n_sets):
         launch(i)
     torch.cuda.synchronize()
