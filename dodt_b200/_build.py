@@ -22,7 +22,7 @@ DIAG_OBJ_DIR = os.path.join(HERE, "_obj_diag")
 DIAG_LIB_PATH = os.path.join(HERE, "libdodt_fe_diag.so")
 
 SOURCES = ["common.cu", "bev_slices.cu", "anchor_filter.cu", "anchor_fused.cu", "crop_resize.cu", "correlation.cu", "correlation_tma.cu",
-           "correlation_feed.cu", "correlation_grad.cu", "nms.cu", "frontend.cu", "anchors.cu", "lidar.cu"]
+           "correlation_feed.cu", "correlation_grad.cu", "nms.cu", "frontend.cu", "anchors.cu", "lidar.cu", "iou3d.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -120,6 +120,7 @@ SIGNATURES = {
                                          c_int32, c_int32, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                          c_void_p, POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dodt_three_d_iou_matrix": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "dodt_nms_workspace_bytes": (c_size_t, [c_int64]),
     "dodt_nms_state_offset": (c_size_t, [c_int64]),
     "dodt_nms": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_float, c_int32, c_int32,

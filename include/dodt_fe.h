@@ -276,6 +276,16 @@ int dodt_emit_detections(const float *boxes, const float *scores, const int32_t 
                          int32_t max_frames, int32_t *row_io, int32_t rewrite, dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Tracking-association IoU: three_d_iou of
+ * wavedata/wavedata/tools/obj_detection/evaluation.py:44-92 for ALL pairs of two box sets, as the
+ * greedy linker of avod/experiments/video_detection*.py needs it per frame (tracks x detections).
+ * boxes_a [na,7], boxes_b [nb,7] f64 rows [ry, l, h, w, tx, ty, tz] (y down, ty = bottom face);
+ * iou [na,nb] f64. The base overlap is clipped exactly; the reference rasterises it at 0.01 m
+ * (evaluation.py:164-261), which moves an IoU by at most ~0.01. All device pointers. */
+int dodt_three_d_iou_matrix(const double *boxes_a, int32_t na, const double *boxes_b, int32_t nb,
+                            double *iou, dodt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * S3 — tf.image.crop_and_resize (TensorFlow 1.3.0 core/kernels/crop_and_resize_op.cc, bilinear),
  * called at avod/core/models/dt_rpn_model.py:418-428 and dt_avod_model.py:253-273.
  * image [batch,H,W,C] f32 NHWC; boxes [n,4] normalised [y1,x1,y2,x2]; box_ind [n] (rows whose

@@ -459,3 +459,109 @@ def non_max_suppression(boxes, scores, max_output_size, iou_threshold=0.5):
         sel[k] = cand
         k += 1
     return sel[:k].astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------
+# (f3) tracking-association IoU
+# ------------------------------------------------------------------------------------------
+
+
+def rotated_bb_corners(box):
+    """wavedata/.../obj_detection/evaluation.py:117-161 (get_rotated_3d_bb) for one box
+    [ry, l, h, w, tx, ty, tz]: the four base corners (x[4], z[4])."""
+    ry, l, _, w, tx, _, tz = (float(v) for v in box)
+    c, s = np.cos(ry), np.sin(ry)
+    xc = l / 2 * np.array([1.0, 1.0, -1.0, -1.0])
+    zc = w / 2 * np.array([1.0, -1.0, -1.0, 1.0])
+    return c * xc + s * zc + tx, -s * xc + c * zc + tz
+
+
+def _clip_polygon(poly, a, b):
+    """Sutherland-Hodgman step: the part of convex polygon `poly` [(x, z)] on the left of (or on)
+    the directed line a -> b."""
+    out = []
+    n = len(poly)
+    for i in range(n):
+        p, q = poly[i], poly[(i + 1) % n]
+        sp = (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0])
+        sq = (b[0] - a[0]) * (q[1] - a[1]) - (b[1] - a[1]) * (q[0] - a[0])
+        if sp >= 0:
+            out.append(p)
+        if (sp >= 0) != (sq >= 0):
+            t = sp / (sp - sq)
+            out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+    return out
+
+
+def rectangle_intersection_area(box, other):
+    """EXACT area of the intersection of the two boxes' rotated bases. The reference
+    (evaluation.py:164-261, get_rectangular_metrics) rasterises both rectangles at 0.01 m with
+    PIL's polygon fill and counts common pixels ("minor precision loss due to discretization"),
+    capped at 100 m^2; this is the quantity it approximates."""
+    xa, za = rotated_bb_corners(box)
+    xb, zb = rotated_bb_corners(other)
+    poly = list(zip(xa, za))
+    clip = list(zip(xb, zb))
+    # orientation of the clip rectangle (the corner order of get_rotated_3d_bb is clockwise in x-z)
+    area2 = sum(clip[i][0] * clip[(i + 1) % 4][1] - clip[(i + 1) % 4][0] * clip[i][1] for i in range(4))
+    if area2 < 0:
+        clip = clip[::-1]
+    for i in range(4):
+        poly = _clip_polygon(poly, clip[i], clip[(i + 1) % 4])
+        if not poly:
+            return 0.0
+    a = 0.0
+    for i in range(len(poly)):
+        a += poly[i][0] * poly[(i + 1) % len(poly)][1] - poly[(i + 1) % len(poly)][0] * poly[i][1]
+    return min(100.0, abs(a) / 2.0)
+
+
+def three_d_iou(box, boxes):
+    """wavedata/.../obj_detection/evaluation.py:44-92 (three_d_iou) with the base intersection
+    computed exactly instead of by rasterisation. box [ry, l, h, w, tx, ty, tz]; boxes [n, 7]."""
+    box = np.asarray(box, dtype=np.float64)
+    boxes = np.asarray(boxes, dtype=np.float64)
+    single = boxes.ndim == 1
+    if single:
+        boxes = boxes[None]
+    box_diag = np.sqrt(box[1] ** 2 + box[2] ** 2 + box[3] ** 2) / 2
+    boxes_diag = np.sqrt(boxes[:, 1] ** 2 + boxes[:, 2] ** 2 + boxes[:, 3] ** 2) / 2
+    dist = np.sqrt(((boxes[:, 4:7] - box[4:7]) ** 2).sum(axis=1))
+    iou = np.zeros(len(boxes))
+    for i in np.flatnonzero(box_diag + boxes_diag >= dist):
+        o = boxes[i]
+        # height_metrics (evaluation.py:95-128): y is down, ty is the BOTTOM of a box
+        h_int = max(0.0, min(box[5], o[5]) - max(box[5] - box[2], o[5] - o[2]))
+        inter = h_int * rectangle_intersection_area(box, o)
+        union = box[1] * box[2] * box[3] + o[1] * o[2] * o[3] - inter
+        iou[i] = inter / union
+    return iou[0] if len(iou) == 1 else iou
+
+
+def track_iou(detections, sigma_l, sigma_h, sigma_iou, t_min, score_fn):
+    """avod/experiments/video_detection.py:235-277 (track_iou), loop for loop, with the pair score
+    (cal_transformed_ious there) passed in: score_fn(last detection of a track, detection).
+    detections: per frame a list of dicts with at least 'scores' and 'frame_id'."""
+    tracks_active, tracks_finished = [], []
+    for detections_frame in detections:
+        if detections_frame == []:
+            continue
+        dets = [det for det in detections_frame if det['scores'] >= sigma_l]
+        updated_tracks = []
+        for track in tracks_active:
+            if len(dets) > 0:
+                ious = [score_fn(track['trajectory'][-1], x) for x in dets]
+                best = int(np.argmax(ious))
+                if ious[best] > sigma_iou:
+                    track['trajectory'].append(dets[best])
+                    track['max_score'] = max(track['max_score'], dets[best]['scores'])
+                    updated_tracks.append(track)
+                    del dets[best]
+            if len(updated_tracks) == 0 or track is not updated_tracks[-1]:
+                if track['max_score'] >= sigma_h and len(track['trajectory']) >= t_min:
+                    tracks_finished.append(track)
+        new_tracks = [{'trajectory': [det], 'max_score': det['scores'], 'start_frame': det['frame_id']}
+                      for det in dets]
+        tracks_active = updated_tracks + new_tracks
+    tracks_finished += [t for t in tracks_active if t['max_score'] >= sigma_h and len(t['trajectory']) >= t_min]
+    return tracks_finished
