@@ -21,9 +21,19 @@ def _ptr(t):
 
 
 def _need_cuda(*tensors):
+    """Every tensor of a call must live on the CURRENT CUDA device: kernels are enqueued on
+    torch.cuda.current_stream(), which belongs to it (wrap the call in torch.cuda.device(...))."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("dodt_b200 runs on CUDA tensors only (there is no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError("tensor on cuda:%d but the current device is cuda:%d: call inside "
+                               "torch.cuda.device(tensor.device)" % (t.device.index, cur))
 
 
 def _dtype_code(t):
