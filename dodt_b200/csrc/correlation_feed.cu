@@ -40,6 +40,7 @@ namespace {
 constexpr int kTW = 64, kTH = 8, kPX = 4;
 constexpr int kThr = kTW / (2 * kPX) * 2 * kTH;   // 128
 constexpr int kMaxPairs = DODT_CORR_STREAM_MAX_PAIRS;
+constexpr int kExclusiveSmem = 116 * 1024;   // > (228 KB - 2 x 1 KB reserved) / 2: two such CTAs never share an SM
 
 // CH: channels per work unit (16: 64-byte pixel vectors, SWIZZLE_64B; 8: 32-byte vectors, SWIZZLE_32B)
 // NST: stages per CTA (unit u lives in stage u % NST and is requested NST units ahead)
@@ -341,11 +342,17 @@ int launch_feed(const float *a, const float *b, int N, int H, int W, int C, int 
       return 1;  // driver without tensor maps: the caller falls back to the cp.async kernel
     for (int k = 1; k < kMaxPairs; ++k) { tm.a[k] = tm.a[0]; tm.b[k] = tm.b[0]; }
   }
-  // the attribute belongs to the (function, device) pair: set it on every launch (cheap)
-  DODT_CUDA_TRY(cudaFuncSetAttribute(corr_feed_k1<R, CH, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   int grid = g.n_tiles < 2 * kNumSMs ? g.n_tiles : 2 * kNumSMs;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;   // persistent CTAs: any count works
-  corr_feed_k1<R, CH, NST><<<grid, kThr, Cfg::SMEM_BYTES, stream>>>(tm, g, out);
+  // A cap at or below the SM count asks for ONE CTA per SM, the other half of every SM (registers,
+  // shared memory) left to the co-running kernels of the frame stream: the launch then requests
+  // more than half of an SM's shared memory, so the block scheduler cannot put two of its CTAs
+  // (or one of a second correlation launch) on the same SM.
+  int smem_bytes = Cfg::SMEM_BYTES;
+  if (max_ctas > 0 && max_ctas <= kNumSMs && smem_bytes < kExclusiveSmem) smem_bytes = kExclusiveSmem;
+  // the attribute belongs to the (function, device) pair: set it on every launch (cheap)
+  DODT_CUDA_TRY(cudaFuncSetAttribute(corr_feed_k1<R, CH, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  corr_feed_k1<R, CH, NST><<<grid, kThr, smem_bytes, stream>>>(tm, g, out);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }

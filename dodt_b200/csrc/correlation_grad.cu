@@ -40,6 +40,7 @@
 // Algorithmic HBM bytes (both gradients, 700x800x32, 25 displacements): read G 56 MB + A, B 2 x 71.68
 // MB, write gA, gB 2 x 71.68 MB = 342.7 MB; the flip pass adds 2 x 70 MB of workspace traffic.
 #include "common.cuh"
+#include "tma_util.cuh"
 
 namespace dodt {
 namespace {
@@ -140,7 +141,8 @@ struct GradCfg {
   static constexpr int B_FLOATS = BH * BPITCH * kCC;          // one stage
   // the coefficient tile is only needed until it sits in registers: it aliases the two stages
   static constexpr int FLOATS = 2 * B_FLOATS > G_FLOATS ? 2 * B_FLOATS : G_FLOATS;
-  static constexpr size_t SMEM = static_cast<size_t>(FLOATS) * sizeof(float);
+  static constexpr size_t BAR_OFF = ((static_cast<size_t>(FLOATS) * sizeof(float) + 127) / 128) * 128;
+  static constexpr size_t SMEM = BAR_OFF + 64;                // + the two full barriers of the TMA feed
 };
 
 // coef [batch, ch, cw, D2]: ch x cw is the extent of the coefficient map; input pixel (y, x) uses
@@ -150,14 +152,28 @@ struct GradCfg {
 // All staging is LDGSTS (cp.async with zero fill = the reference's padding): the copies of a phase
 // are in flight together, and chunk c+1 of the other input lands while chunk c is consumed.
 // GB = bytes per coefficient copy (8 when every tile row starts 8-byte aligned, else 4).
-template <int R, bool REV, int GB>
+// TMA: the other input's tiles arrive by cp.async.bulk.tensor (UTMALDG) issued by one thread and
+// completing on an mbarrier, zero fill by the TMA unit (round 2: the forward kernel's feed);
+// otherwise by LDGSTS from every thread (round 1; kept for hosts without tensor maps).
+template <int R, bool REV, int GB, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2)
-corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, int batch, int H, int W,
-             int C, int ch, int cw, int cshift, int tiles_x, int tiles_y, float *__restrict__ dst) {
+corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, const __grid_constant__ CUtensorMap map_other,
+             int batch, int H, int W, int C, int ch, int cw, int cshift, int tiles_x, int tiles_y,
+             float *__restrict__ dst) {
   using Cfg = GradCfg<R>;
   constexpr int WN = Cfg::WN, D2 = Cfg::D2, NB = kPX + 2 * R;
   constexpr int GE = GB / 4;            // floats per coefficient copy
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(1024) float smem[];
+  const uint32_t bar_full = tma::smem_u32(reinterpret_cast<unsigned char *>(smem) + Cfg::BAR_OFF);
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      tma::mbar_init(bar_full, 1);
+      tma::mbar_init(bar_full + 8, 1);
+      tma::mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  unsigned it = 0;                      // chunks consumed so far by this CTA (TMA: stage / phase)
   float *sg = smem;                     // [kTH][G_PITCH], dead once gk[] is loaded
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // lane bits: [0] parity, [1..2] row & 3, [3..4] group & 3; warps tile 2 (rows) x 2 (x halves)
@@ -218,6 +234,13 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, in
     // index leaves the bank swizzle of smem_off unchanged).
     const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
     const int lhalf = lx & 1, lpx = lx >> 1;
+    auto issue_tma = [&](int chunk, unsigned u) {   // thread 0: chunk `chunk` of this tile is unit u
+      const uint32_t bar = bar_full + 8 * (u & 1);
+      tma::fence_proxy_async();
+      tma::mbar_expect_tx(bar, Cfg::B_FLOATS * 4);
+      tma::load_4d(tma::smem_u32(smem + (u & 1) * Cfg::B_FLOATS), &map_other, chunk * kCC, tx0 - Cfg::HALO,
+                   ty0 - Cfg::HALO, n, bar);
+    };
     auto issue = [&](int chunk) {
       float *sb = smem + (chunk & 1) * Cfg::B_FLOATS;
       const int c0 = chunk * kCC + 4 * lhalf;
@@ -243,16 +266,27 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, in
       }
       cp_async_commit();
     };
-    issue(0);
-    for (int chunk = 0; chunk < n_chunks; ++chunk) {
-      if (chunk + 1 < n_chunks) {
-        issue(chunk + 1);       // its stage was released by the barrier that ended chunk - 1
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
+    if (TMA) {
+      if (threadIdx.x == 0) {
+        issue_tma(0, it);
+        if (n_chunks > 1) issue_tma(1, it + 1);
       }
-      __syncthreads();
-      const float *sb = smem + (chunk & 1) * Cfg::B_FLOATS;
+    } else {
+      issue(0);
+    }
+    for (int chunk = 0; chunk < n_chunks; ++chunk, ++it) {
+      if (TMA) {
+        tma::mbar_wait(bar_full + 8 * (it & 1), (it >> 1) & 1);
+      } else {
+        if (chunk + 1 < n_chunks) {
+          issue(chunk + 1);       // its stage was released by the barrier that ended chunk - 1
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncthreads();
+      }
+      const float *sb = smem + ((TMA ? it : static_cast<unsigned>(chunk)) & 1) * Cfg::B_FLOATS;
       const int c0 = chunk * kCC;
 
       float4 acc[kPX][2];
@@ -306,7 +340,8 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, in
           }
         }
       }
-      __syncthreads();   // stage (chunk & 1) may be refilled by issue(chunk + 2)
+      __syncthreads();   // the stage may be refilled (cp.async: by issue(chunk + 2) of the next round)
+      if (TMA && threadIdx.x == 0 && chunk + 2 < n_chunks) issue_tma(chunk + 2, it + 2);
     }
   }
 }
@@ -381,12 +416,21 @@ int launch_k1(const float *grad, const float *a, const float *b, const GradGeom 
   const long long n_tiles = static_cast<long long>(tiles_x) * tiles_y * g.batch;
   if (n_tiles > 0x7FFFFFFFll) return 1;
   const int grid = static_cast<int>(n_tiles < 2 * kNumSMs ? n_tiles : 2 * kNumSMs);
-  auto run = [&](auto kernel, const float *coef, const float *other, int ch, int cw, int cshift,
-                 float *dst) -> int {
-    DODT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(Cfg::SMEM)));
-    kernel<<<grid, kThreads, Cfg::SMEM, stream>>>(coef, other, g.batch, g.H, g.W, g.C, ch, cw, cshift,
-                                                  tiles_x, tiles_y, dst);
+  auto run = [&](auto kernel_tma, auto kernel_ldgsts, const float *coef, const float *other, int ch, int cw,
+                 int cshift, float *dst) -> int {
+    alignas(64) CUtensorMap map;
+    const bool use_tma = tma::make_nhwc_map<kCC>(&map, other, g.batch, g.H, g.W, g.C, Cfg::BPITCH, Cfg::BH);
+    if (use_tma) {
+      DODT_CUDA_TRY(cudaFuncSetAttribute(kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::SMEM)));
+      kernel_tma<<<grid, kThreads, Cfg::SMEM, stream>>>(coef, other, map, g.batch, g.H, g.W, g.C, ch, cw, cshift,
+                                                        tiles_x, tiles_y, dst);
+    } else {
+      DODT_CUDA_TRY(cudaFuncSetAttribute(kernel_ldgsts, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::SMEM)));
+      kernel_ldgsts<<<grid, kThreads, Cfg::SMEM, stream>>>(coef, other, map, g.batch, g.H, g.W, g.C, ch, cw,
+                                                           cshift, tiles_x, tiles_y, dst);
+    }
     DODT_AFTER_LAUNCH();
     return DODT_OK;
   };
@@ -396,8 +440,10 @@ int launch_k1(const float *grad, const float *a, const float *b, const GradGeom 
   };
   if (ga) {
     const int rc = wide(grad, g.out_w, shift)
-                       ? run(corr_grad_k1<R, false, 8>, grad, b, g.out_h, g.out_w, shift, ga)
-                       : run(corr_grad_k1<R, false, 4>, grad, b, g.out_h, g.out_w, shift, ga);
+                       ? run(corr_grad_k1<R, false, 8, true>, corr_grad_k1<R, false, 8, false>, grad, b, g.out_h,
+                             g.out_w, shift, ga)
+                       : run(corr_grad_k1<R, false, 4, true>, corr_grad_k1<R, false, 4, false>, grad, b, g.out_h,
+                             g.out_w, shift, ga);
     if (rc != DODT_OK) return rc;
   }
   if (gb) {
@@ -411,8 +457,9 @@ int launch_k1(const float *grad, const float *a, const float *b, const GradGeom 
     dim3 fgrid(ceil_div(g.W, kFW), ceil_div(g.H, kFH), g.batch);
     flip<<<fgrid, kFlipThreads, fsmem, stream>>>(grad, g.out_h, g.out_w, g.H, g.W, shift, ws);
     DODT_AFTER_LAUNCH();
-    const int rc = wide(ws, g.W, 0) ? run(corr_grad_k1<R, true, 8>, ws, a, g.H, g.W, 0, gb)
-                                    : run(corr_grad_k1<R, true, 4>, ws, a, g.H, g.W, 0, gb);
+    const int rc = wide(ws, g.W, 0)
+                       ? run(corr_grad_k1<R, true, 8, true>, corr_grad_k1<R, true, 8, false>, ws, a, g.H, g.W, 0, gb)
+                       : run(corr_grad_k1<R, true, 4, true>, corr_grad_k1<R, true, 4, false>, ws, a, g.H, g.W, 0, gb);
     if (rc != DODT_OK) return rc;
   }
   return DODT_OK;

@@ -55,6 +55,7 @@ class FrontEndConfig:
                                                     # for the RPN NMS in a graph; a frame that needs more
                                                     # reports n_top[1] == 0 and is finished by
                                                     # FrontEnd.complete_frame
+    corr_pairs_per_launch: int = 8                  # consecutive pairs per frame-stream S4 launch
     corr_max_ctas: int = 0                          # CTA cap of the correlation launch (0 = none: two
                                                     # persistent CTAs per SM). 148 (one per SM, the other
                                                     # half of each SM left to neighbouring frames) is ~2 %
@@ -278,23 +279,36 @@ class FrontEnd:
         self.side_stream.wait_stream(main)
         for st in lanes[1:]:
             st.wait_stream(main)
+        # S4: launches of up to corr_pairs_per_launch consecutive pairs, back to back on the side
+        # stream; frame j waits for the launch that holds its pair only
+        P = max(1, min(int(c.corr_pairs_per_launch), 8))
+        corr_done = [None] * k
         if "S4" not in skip:
             with torch.cuda.stream(self.side_stream):
-                if k == 1:
-                    ops.correlation(prev_slot.bev_feat, slots[0].bev_feat, 1, c.corr_max_displacement, 1,
-                                    c.corr_stride_2, c.corr_padding, out=slots[0].corr,
-                                    max_ctas=c.corr_max_ctas)
-                else:
-                    ops.correlation_stream([prev_slot.bev_feat] + [s.bev_feat for s in slots], 1,
-                                           c.corr_max_displacement, 1, c.corr_stride_2, c.corr_padding,
-                                           outs=[s.corr for s in slots], max_ctas=c.corr_max_ctas)
+                for j0 in range(0, k, P):
+                    grp = slots[j0:j0 + P]
+                    prev = prev_slot if j0 == 0 else slots[j0 - 1]
+                    if len(grp) == 1:
+                        ops.correlation(prev.bev_feat, grp[0].bev_feat, 1, c.corr_max_displacement, 1,
+                                        c.corr_stride_2, c.corr_padding, out=grp[0].corr,
+                                        max_ctas=c.corr_max_ctas)
+                    else:
+                        ops.correlation_stream([prev.bev_feat] + [s.bev_feat for s in grp], 1,
+                                               c.corr_max_displacement, 1, c.corr_stride_2, c.corr_padding,
+                                               outs=[s.corr for s in grp], max_ctas=c.corr_max_ctas)
+                    ev = torch.cuda.Event()
+                    ev.record(self.side_stream)
+                    for j in range(j0, min(j0 + P, k)):
+                        corr_done[j] = ev
         for s, st in zip(slots, lanes):
             with torch.cuda.stream(st):
                 self._enqueue_pre(s, skip)
-        for s, st in zip(slots, lanes):
+        for j, (s, st) in enumerate(zip(slots, lanes)):
             with torch.cuda.stream(st):
-                st.wait_stream(self.side_stream)          # S3b: the corr crop needs S4
+                if corr_done[j] is not None:
+                    st.wait_event(corr_done[j])           # S3b: the corr crop needs this frame's S4
                 self._enqueue_post(s, block, skip)
+        main.wait_stream(self.side_stream)
         for st in lanes[1:]:
             main.wait_stream(st)
         return ops.launch_count() - before
