@@ -51,6 +51,9 @@ def parse():
                     help="consecutive frames per CUDA graph: their correlations share one launch")
     ap.add_argument("--corr-ctas", type=int, default=None,
                     help="CTA cap of the correlation launch inside the frame runner (default: FrontEndConfig)")
+    ap.add_argument("--n-sequences", type=int, default=8,
+                    help="--workload sequences: how many of the 8 sequences to run (fewer sequences than ranks "
+                         "exercises shard.plan's contiguous chunks with a one-frame halo)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -230,7 +233,7 @@ def run_sequences_region(args, fe, slots, hosts, graphs, streams, main, block_un
     import torch.distributed as dist
 
     from dodt_b200 import shard
-    lengths = SEQUENCE_LENGTHS
+    lengths = SEQUENCE_LENGTHS[:max(1, min(args.n_sequences, len(SEQUENCE_LENGTHS)))]
     plan = shard.plan(lengths, world, rank)
     # work list: groups of G consecutive frames of one plan item, ids (-1, -1) for halo / padding
     groups = []
