@@ -127,7 +127,10 @@ struct FeedMaps {
   CUtensorMap b[kMaxPairs];
 };
 
-template <int R, int CH, int NST>
+// SQ: a thread owns 2 x 2 pixels (spaced 2 apart in both directions) instead of 4 in a row: the
+// B positions its (pixel, displacement) pairs need shrink from 8 x WN to (WN+1) x (WN+1) per
+// 4-channel step (36 instead of 40 LDS.128 at R = 2), same 4 x WN^2 accumulators, same bits.
+template <int R, int CH, int NST, bool SQ>
 __global__ void __launch_bounds__(kThr, 2)
 corr_feed_k1(const __grid_constant__ FeedMaps maps, const __grid_constant__ FeedGeom g, float *__restrict__ out) {
   using Cfg = FeedCfg<R, CH, NST>;
@@ -173,14 +176,31 @@ corr_feed_k1(const __grid_constant__ FeedMaps maps, const __grid_constant__ Feed
     tma_load_4d(stage_base + Cfg::A_BYTES, mb, ch * kCH, ax - Cfg::HALO, ay - Cfg::HALO, item, bar);
   };
 
-  // ---- compute role: lane bits [0] parity, [1..2] row & 3, [3..4] group & 3
-  const int row = (warp / kWX) * 4 + ((lane >> 1) & 3);
-  const int x0 = ((warp % kWX) * 4 + (lane >> 3)) * (2 * kPX) + (lane & 1);
-  int aoff[kPX], boff[NB];
+  // ---- compute role
+  // row tile:    lane bits [0] parity, [1..2] row & 3, [3..4] group & 3; pixels (row, x0 + 2j)
+  // square tile: lane bits [0] x parity, [1] g & 1, [2] y0 & 1, [3..4] (g >> 1) & 3, warp bits [0] g >> 3,
+  //              [1] y0 >> 2; pixels (row + 2 iy, x0 + 2 ix), x0 = 4 g + parity, row in {0, 1, 4, 5}.
+  // Either way the eight lanes of a quarter-warp read eight pixels whose indices differ mod 8
+  // (pitches are 2 mod 8), i.e. eight different 16-byte bank groups under the swizzle.
+  constexpr int NBQ = SQ ? WN + 1 : NB;            // B columns a thread reads per B row
+  constexpr int NBR = SQ ? WN + 1 : WN;            // B rows a thread reads per 4-channel step
+  int row, x0;
+  if constexpr (SQ) {
+    const int g4 = ((lane >> 1) & 1) | (((lane >> 3) & 3) << 1) | ((warp & 1) << 3);
+    row = ((warp >> 1) << 2) | ((lane >> 2) & 1);
+    x0 = 4 * g4 + (lane & 1);
+  } else {
+    row = (warp / kWX) * 4 + ((lane >> 1) & 3);
+    x0 = ((warp % kWX) * 4 + (lane >> 3)) * (2 * kPX) + (lane & 1);
+  }
+  // pixel j of the thread: row tile (row, x0 + 2j); square tile (row + 2 (j >> 1), x0 + 2 (j & 1))
+  auto px_row = [&](int j) { return SQ ? row + 2 * (j >> 1) : row; };
+  auto px_col = [&](int j) { return SQ ? x0 + 2 * (j & 1) : x0 + 2 * j; };
+  int aoff[kPX], boff[NBQ];
 #pragma unroll
-  for (int j = 0; j < kPX; ++j) aoff[j] = swz<CH>(row * Cfg::AW + x0 + 2 * j);
+  for (int j = 0; j < kPX; ++j) aoff[j] = swz<CH>(px_row(j) * Cfg::AW + px_col(j));
 #pragma unroll
-  for (int q = 0; q < NB; ++q) boff[q] = swz<CH>(row * Cfg::BW + x0 + 2 * q);
+  for (int q = 0; q < NBQ; ++q) boff[q] = swz<CH>(row * Cfg::BW + x0 + 2 * q);
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -209,25 +229,30 @@ corr_feed_k1(const __grid_constant__ FeedMaps maps, const __grid_constant__ Feed
         for (int j = 0; j < kPX; ++j)
           va[j] = *reinterpret_cast<const float4 *>(sa + (aoff[j] ^ (cv << 2)));
 #pragma unroll
-        for (int p = 0; p < WN; ++p) {
-          float4 vb[NB];
-          // rows advance by 2*BW = 148 pixels: (pixel >> 1) & 3 advances by 2 per p, i.e. bit 1 of the
-          // swizzle term flips with every odd p; the rest of the offset is a compile-time constant
+        for (int br = 0; br < NBR; ++br) {
+          float4 vb[NBQ];
+          // rows advance by 2*BW = 148 pixels: the swizzle term of a pixel flips with every odd br;
+          // the rest of the offset is a compile-time constant
 #pragma unroll
-          for (int q = 0; q < NB; ++q)
+          for (int q = 0; q < NBQ; ++q)
             vb[q] = *reinterpret_cast<const float4 *>(
-                sb + (boff[q] ^ ((row_flip<CH>(p) ^ cv) << 2)) + p * 2 * Cfg::BW * kCH);
+                sb + (boff[q] ^ ((row_flip<CH>(br) ^ cv) << 2)) + br * 2 * Cfg::BW * kCH);
 #pragma unroll
-          for (int j = 0; j < kPX; ++j)
+          for (int j = 0; j < kPX; ++j) {
+            // square tile: B row br serves displacement row p = br - iy of pixel row iy
+            const int p = SQ ? br - (j >> 1) : br;
+            const int jc = SQ ? (j & 1) : j;
+            if (p < 0 || p >= WN) continue;
 #pragma unroll
             for (int o = 0; o < WN; ++o) {
               float s = acc[j][p * WN + o];
-              s = fmaf(va[j].x, vb[j + o].x, s);
-              s = fmaf(va[j].y, vb[j + o].y, s);
-              s = fmaf(va[j].z, vb[j + o].z, s);
-              s = fmaf(va[j].w, vb[j + o].w, s);
+              s = fmaf(va[j].x, vb[jc + o].x, s);
+              s = fmaf(va[j].y, vb[jc + o].y, s);
+              s = fmaf(va[j].z, vb[jc + o].z, s);
+              s = fmaf(va[j].w, vb[jc + o].w, s);
               acc[j][p * WN + o] = s;
             }
+          }
         }
       }
       __syncthreads();   // everyone is done reading the stage
@@ -242,7 +267,7 @@ corr_feed_k1(const __grid_constant__ FeedMaps maps, const __grid_constant__ Feed
     if (g.pow2) {
 #pragma unroll
       for (int j = 0; j < kPX; ++j) {
-        float *dst = stg + row * Cfg::OUT_PITCH + (x0 + 2 * j) * D2;
+        float *dst = stg + px_row(j) * Cfg::OUT_PITCH + px_col(j) * D2;
 #pragma unroll
         for (int k = 0; k < D2; ++k) dst[k] = __fmul_rn(acc[j][k], g.inv_c);   // exact: 1/2^k
       }
@@ -250,7 +275,7 @@ corr_feed_k1(const __grid_constant__ FeedMaps maps, const __grid_constant__ Feed
       const float sumelems = static_cast<float>(g.C);
 #pragma unroll
       for (int j = 0; j < kPX; ++j) {
-        float *dst = stg + row * Cfg::OUT_PITCH + (x0 + 2 * j) * D2;
+        float *dst = stg + px_row(j) * Cfg::OUT_PITCH + px_col(j) * D2;
 #pragma unroll
         for (int k = 0; k < D2; ++k) dst[k] = __fdiv_rn(acc[j][k], sumelems);
       }
@@ -314,7 +339,7 @@ bool make_map(CUtensorMap *map, const float *ptr, int N, int H, int W, int C, in
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int R, int CH, int NST>
+template <int R, int CH, int NST, bool SQ = true>
 int launch_feed(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w, int shift,
                 float *out, int max_ctas, cudaStream_t stream, const float *const *maps, float *const *outs) {
   using Cfg = FeedCfg<R, CH, NST>;
@@ -351,8 +376,8 @@ int launch_feed(const float *a, const float *b, int N, int H, int W, int C, int 
   int smem_bytes = Cfg::SMEM_BYTES;
   if (max_ctas > 0 && max_ctas <= kNumSMs && smem_bytes < kExclusiveSmem) smem_bytes = kExclusiveSmem;
   // the attribute belongs to the (function, device) pair: set it on every launch (cheap)
-  DODT_CUDA_TRY(cudaFuncSetAttribute(corr_feed_k1<R, CH, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  corr_feed_k1<R, CH, NST><<<grid, kThr, smem_bytes, stream>>>(tm, g, out);
+  DODT_CUDA_TRY(cudaFuncSetAttribute(corr_feed_k1<R, CH, NST, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  corr_feed_k1<R, CH, NST, SQ><<<grid, kThr, smem_bytes, stream>>>(tm, g, out);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }
@@ -366,7 +391,8 @@ bool feed_applies(int C, int out_h, int out_w, int H, int W) {
 }
 
 // diagnostic build: DODT_CORR_FEED = 1 -> 8-channel units, two stages; 2 -> 16-channel units, one stage;
-// 3 / 4 -> 8-channel units, four / three stages (one CTA per SM)
+// 3 / 4 -> 8-channel units, four / three stages (one CTA per SM); 5 -> the product configuration with the
+// 4 x 1 pixel tile of round 1 instead of 2 x 2
 template <int R>
 int launch_variant(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w, int shift,
                    float *out, int max_ctas, cudaStream_t stream, const float *const *maps, float *const *outs) {
@@ -376,6 +402,7 @@ int launch_variant(const float *a, const float *b, int N, int H, int W, int C, i
   if (v == 2) return launch_feed<R, 16, 1>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream, maps, outs);
   if (v == 3) return launch_feed<R, 8, 4>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream, maps, outs);
   if (v == 4) return launch_feed<R, 8, 3>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream, maps, outs);
+  if (v == 5) return launch_feed<R, kFeedCH, kFeedNST, false>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream, maps, outs);
 #endif
   return launch_feed<R, kFeedCH, kFeedNST>(a, b, N, H, W, C, out_h, out_w, shift, out, max_ctas, stream, maps, outs);
 }
