@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--n-sequences", type=int, default=8,
                     help="--workload sequences: how many of the 8 sequences to run (fewer sequences than ranks "
                          "exercises shard.plan's contiguous chunks with a one-frame halo)")
+    ap.add_argument("--cpu-workers", type=int, default=0,
+                    help="processes of the CPU arm (default: one per host core, at most 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -116,6 +118,8 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))         # one frame per core (about 1 GB of inputs each)
+    if args.cpu_workers > 0:
+        workers = args.cpu_workers
     steps = max(1, min(args.steps, 6))       # bounded: a CPU frame takes seconds
     warmup = min(args.warmup, 1)
     r = cpu_arm(steps, warmup, workers)
