@@ -404,6 +404,7 @@ def run_dense(args):
             main.wait_stream(st)
 
     K, Wm = max(args.steps, 1), max(args.warmup, 3)
+    SW = 8                                  # sweeps of the buffer sets per step (64 frames)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -416,13 +417,13 @@ def run_dense(args):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     a.record()
-    sweeps(g_all, K)
+    sweeps(g_all, K * SW)
     b.record()
     torch.cuda.synchronize()
     sampler.window = (w0, time.time())
     ms = a.elapsed_time(b)
     clocks = sampler.stop() if rank == 0 else None
-    fps = K * n_sets / (ms / 1e3)
+    fps = K * SW * n_sets / (ms / 1e3)
 
     def stage_us(fn):
         gs = graphs_of(fn)
@@ -441,13 +442,13 @@ def run_dense(args):
     if rank == 0:
         print(json.dumps({
             "metric": "front-end frames/sec", "value": fps * world, "unit": "frames/s", "n_gpus": world, "steps": K,
-            "warmup": Wm, "ms_per_step": ms / K, "frames_per_step": n_sets, "higher_is_better": True,
+            "warmup": Wm, "ms_per_step": ms / K, "frames_per_step": n_sets * SW, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 binning/predicates, i32 counts)",
             "data": "synthetic",
             "config": {"workload": "configs[4] dense 128-beam LiDAR: %d points, %.2f m BEV %dx%dx%d (S1) + integral "
                                    "image and %d-anchor filter (S2)" % (n_pts, voxel, nz, nx, S + 1, nA),
-                       "step": "one sweep of %d resident buffer sets (%.0f MB of maps each, > 126 MB L2 together)"
-                               % (n_sets, 4 * (S + 1) * nx * nz / 1e6),
+                       "step": "%d sweeps of %d resident buffer sets (%.0f MB of maps each, > 126 MB L2 together)"
+                               % (SW, n_sets, 4 * (S + 1) * nx * nz / 1e6),
                        "anchors_kept": int(sets[0]["n_kept"].item()), "occupied_cells": int(sets[0]["occ"].sum())},
             "roofline": {"bound": "hbm", "kernel": "bev_clear + bev_accumulate + bev_resolve_scan (S1)",
                          "achieved": b1 / t1 / 1e3, "peak": peak, "unit": "GB/s", "frac": b1 / t1 / 1e3 / peak,
@@ -456,7 +457,7 @@ def run_dense(args):
                                 "achieved": b2 / t2 / 1e3, "frac": b2 / t2 / 1e3 / peak},
                          "frame": {"algorithmic_bytes": b1 + b2, "achieved": (b1 + b2) * fps / 1e9,
                                    "frac": (b1 + b2) * fps / 1e9 / peak}},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": launches * n_sets * K,
+            "cpu_baseline": None, "e2e": None, "gpu_launches": launches * n_sets * K * SW,
             "launches_per_frame": launches, "clocks": clocks,
         }))
 
