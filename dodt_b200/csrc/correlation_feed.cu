@@ -5,34 +5,42 @@
 // Why this kernel exists (tools/micro/feed_bench.cu, profiles/r02_feed_bench.txt): feeding an SM
 // with the tiles of an NHWC map costs 37 us per pair with 16-byte cp.async on 32-byte pieces (the
 // round-1 loader: an 8-channel chunk of a pixel is one sector of its 128-byte line, 16 lines per
-// warp instruction), 30.8 us with tensor-TMA boxes whose inner row is 32 bytes, but 18.5 us with
-// 64-byte inner rows and 16.5 us with 128-byte ones. So the channel chunk is 16 channels here:
+// warp instruction, every thread spending issue slots and L1TEX wavefronts on copies), 30.8 us with
+// tensor-TMA boxes whose inner row is 32 bytes, 18.5 / 16.5 us with 64- / 128-byte inner rows. A
+// thread's register tile (100 accumulators) caps the SM at 256 threads, and a 16-channel unit of an
+// 8 x 64 tile is 107 KB: only one stage per CTA fits and a CTA cannot refill the stage it reads
+// (measured 43.4 us per pair, a third of the warp samples in the mbarrier wait). Prefetch depth
+// beats feed rate: the product configuration is
 //
-//   feed      one elected thread issues two cp.async.bulk.tensor.4d loads (UTMALDG) per work unit
-//             (an 8 x 64-pixel output tile x 16 channels): the A tile [8 x 66 px] and the B tile
-//             with its 4-pixel halo [16 x 74 px], 64-byte pixel vectors under SWIZZLE_64B, into the
-//             CTA's single 107 KB stage. Out-of-image elements are zero-filled by the TMA unit,
-//             which IS the reference's zero padding (PadData and the two padded temporaries of
-//             pad.cu.cc / correlation_kernel.cc:69-107 never exist). Completion arrives on an
-//             mbarrier (complete_tx). No thread spends issue slots or L1TEX wavefronts on copies.
-//   overlap   two CTAs per SM, one stage each: while one CTA computes a unit the other's unit is
-//             in flight (a CTA cannot refill its own stage while it reads it).
-//   math      as round 1: a thread owns 4 pixels spaced 2 apart on one row and all (2R+1)^2
+//   feed      8-channel units (an 8 x 64-pixel output tile x 8 channels) in a TWO-stage ring: one
+//             elected thread issues two cp.async.bulk.tensor.4d loads (UTMALDG) per unit — the A
+//             tile [8 x 66 px] and the B tile with its 4-pixel halo [16 x 74 px], 32-byte pixel
+//             vectors under SWIZZLE_32B — two units ahead of their use. Out-of-image elements are
+//             zero-filled by the TMA unit, which IS the reference's zero padding (PadData and the
+//             two padded temporaries of pad.cu.cc / correlation_kernel.cc:69-107 never exist).
+//             Completion arrives on an mbarrier (complete_tx). No thread issues a copy.
+//   overlap   two CTAs per SM; one __syncthreads per unit hands the consumed stage back (warps
+//             that free-run and return stages through a counter measured slower: 38.0 vs 36.5 us).
+//   math      a thread owns 2 x 2 pixels spaced 2 apart in both directions and all (2R+1)^2
 //             displacements of each (100 fp32 accumulators at R = 2) across the channel chunks;
-//             per displacement row it reads 8 B-pixel float4s from shared memory and feeds 20
-//             (pixel, displacement) pairs. Tile pitches are 2 (mod 8) pixels, so with the 64-byte
-//             swizzle the eight lanes of a quarter-warp hit eight different 16-byte bank groups.
-//   epilogue  the finished tile (8 x 64 px x 25 floats) is staged through the stage and written
+//             per B row it reads 6 B-pixel float4s from shared memory (36 + 4 LDS.128 per 400
+//             FFMA; the 4 x 1 tile of round 1, kept as an A/B instantiation, needs 40 + 4). Tile
+//             pitches are 2 (mod 8) pixels, so under the swizzle the eight lanes of a quarter-warp
+//             hit eight different 16-byte bank groups.
+//   epilogue  the finished tile (8 x 64 px x 25 floats) is staged through the stage just consumed
+//             (the next tile's first unit is already in flight in the other stage) and written
 //             to HBM as coalesced rows.
 //
 // Summation order per output element: channels in ascending order, one fused multiply-add each,
 // the same as corr_async_k1 (correlation_tma.cu) — results are bit-identical to it.
 //
 // Algorithmic HBM bytes per launch: 2*H*W*C*4 read once + H*W*D^2*4 written once (199.36 MB at
-// 700x800x32, D^2 = 25); halo re-reads are served by the 126 MB L2.
+// 700x800x32, D^2 = 25); halo re-reads are served by the 126 MB L2. 35.9 us per pair in the 8-pair
+// frame-stream launch (profiles/r02_corr_feed_ncu.txt: shared-memory pipe 77 %, DRAM 54 %).
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tma_util.cuh"
 
 namespace dodt {
 namespace {
@@ -65,38 +73,6 @@ struct FeedCfg {
   static_assert(OUT_BYTES <= STAGE_BYTES, "output staging fits the stage");
   static_assert(AW % 8 == 2 && BW % 8 == 2, "pitches 2 (mod 8) keep float4 reads conflict-free");
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c0, int c1,
-                                            int c2, int c3, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%2, %3, %4, %5}], [%6];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
-      "r"(bar)
-      : "memory");
-}
 
 // 64-byte pixel vectors under CU_TENSOR_MAP_SWIZZLE_64B: bits [4,5] of the byte offset are XORed
 // with bits [7,8], i.e. the 16-byte piece `c` of pixel p sits at piece c ^ ((p >> 1) & 3).
@@ -140,15 +116,15 @@ corr_feed_k1(const __grid_constant__ FeedMaps maps, const __grid_constant__ Feed
   constexpr int kWarps = kThr / 32;
   constexpr int kWX = kTW / (8 * kPX);                  // warps along x
   extern __shared__ __align__(1024) unsigned char smem[];
-  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t smem_base = tma::smem_u32(smem);
   const uint32_t bar_full = smem_base + Cfg::BAR_OFF;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_chunks = g.C / kCH;
 
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < NST; ++s) mbar_init(bar_full + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < NST; ++s) tma::mbar_init(bar_full + 8 * s, 1);
+    tma::mbar_fence_init();
   }
   __syncthreads();
 
@@ -170,10 +146,10 @@ corr_feed_k1(const __grid_constant__ FeedMaps maps, const __grid_constant__ Feed
     const CUtensorMap *mb = g.n_stream ? &maps.b[n] : &maps.b[0];
     const int item = g.n_stream ? 0 : n;
     // the stage was read (math) or written (output staging) through the generic proxy
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(bar, Cfg::STAGE_BYTES);
-    tma_load_4d(stage_base, ma, ch * kCH, ax, ay, item, bar);
-    tma_load_4d(stage_base + Cfg::A_BYTES, mb, ch * kCH, ax - Cfg::HALO, ay - Cfg::HALO, item, bar);
+    tma::fence_proxy_async();
+    tma::mbar_expect_tx(bar, Cfg::STAGE_BYTES);
+    tma::load_4d(stage_base, ma, ch * kCH, ax, ay, item, bar);
+    tma::load_4d(stage_base + Cfg::A_BYTES, mb, ch * kCH, ax - Cfg::HALO, ay - Cfg::HALO, item, bar);
   };
 
   // ---- compute role
@@ -221,7 +197,7 @@ corr_feed_k1(const __grid_constant__ FeedMaps maps, const __grid_constant__ Feed
       stage = it % NST;
       const float *sa = reinterpret_cast<const float *>(smem + stage * Cfg::STAGE_PITCH);
       const float *sb = sa + Cfg::A_BYTES / 4;
-      mbar_wait(bar_full + 8 * stage, (it / NST) & 1);
+      tma::mbar_wait(bar_full + 8 * stage, (it / NST) & 1);
 #pragma unroll
       for (int cv = 0; cv < kCH / 4; ++cv) {
         float4 va[kPX];
@@ -302,43 +278,6 @@ corr_feed_k1(const __grid_constant__ FeedMaps maps, const __grid_constant__ Feed
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
-                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    else
-      (void)cudaGetLastError();
-  }
-  return fn;
-}
-
-// NHWC fp32 image(s) as a 4-D tensor (C, W, H, N); box = (16 channels, box_w px, box_h rows, 1)
-template <int CH>
-bool make_map(CUtensorMap *map, const float *ptr, int N, int H, int W, int C, int box_w, int box_h) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return false;
-  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W),
-                              static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
-  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4,
-                                 static_cast<cuuint64_t>(H) * W * C * 4};
-  const cuuint32_t box[4] = {CH, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(ptr), dims, strides, box,
-             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CH == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
-             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int R, int CH, int NST, bool SQ = true>
 int launch_feed(const float *a, const float *b, int N, int H, int W, int C, int out_h, int out_w, int shift,
                 float *out, int max_ctas, cudaStream_t stream, const float *const *maps, float *const *outs) {
@@ -356,14 +295,14 @@ int launch_feed(const float *a, const float *b, int N, int H, int W, int C, int 
   if (maps) {   // frame-stream form: N pairs over N + 1 images
     g.n_stream = N;
     for (int k = 0; k < N; ++k) {
-      if (!make_map<CH>(&tm.a[k], maps[k], 1, H, W, C, Cfg::AW, kTH) ||
-          !make_map<CH>(&tm.b[k], maps[k + 1], 1, H, W, C, Cfg::BW, Cfg::BH))
+      if (!tma::make_nhwc_map<CH>(&tm.a[k], maps[k], 1, H, W, C, Cfg::AW, kTH) ||
+          !tma::make_nhwc_map<CH>(&tm.b[k], maps[k + 1], 1, H, W, C, Cfg::BW, Cfg::BH))
         return 1;
       g.outs[k] = outs[k];
     }
     for (int k = N; k < kMaxPairs; ++k) { tm.a[k] = tm.a[0]; tm.b[k] = tm.b[0]; }
   } else {
-    if (!make_map<CH>(&tm.a[0], a, N, H, W, C, Cfg::AW, kTH) || !make_map<CH>(&tm.b[0], b, N, H, W, C, Cfg::BW, Cfg::BH))
+    if (!tma::make_nhwc_map<CH>(&tm.a[0], a, N, H, W, C, Cfg::AW, kTH) || !tma::make_nhwc_map<CH>(&tm.b[0], b, N, H, W, C, Cfg::BW, Cfg::BH))
       return 1;  // driver without tensor maps: the caller falls back to the cp.async kernel
     for (int k = 1; k < kMaxPairs; ++k) { tm.a[k] = tm.a[0]; tm.b[k] = tm.b[0]; }
   }
