@@ -317,3 +317,18 @@ def test_lidar_ingest_against_reference_outputs():
     full = O.lidar_in_camera_view(g["velo"], g["r0_rect"], g["tr_velodyne_to_cam"], g["p2"])
     np.testing.assert_allclose(full[:, ::7], g["full_every_7th"], rtol=1e-13, atol=1e-13)
     np.testing.assert_array_equal(g["fov"], _load("s1s2_kitti_000003.npz")["points"])
+
+
+def test_kitti_like_cloud_has_the_surveyed_occupancy():
+    """synth.point_cloud_kitti (bench.py --workload kitti) lands in the ranges SURVEY 8(d) measured on
+    the reference's real KITTI tracking frames: 16-20 k points, 9.3-15.1 k of 89 600 anchors kept by
+    the empty-anchor filter (the evenly spread benchmark cloud keeps ~60 k), a few thousand occupied
+    cells in the 0.2-2.0 m slice."""
+    a = S.car_anchors()
+    for frame in (0, 5):
+        pc = S.point_cloud_kitti(2, frame).astype(np.float64)
+        assert 16000 <= pc.shape[1] <= 20500
+        occ, vox = O.occupancy_grid(pc, S.GROUND_PLANE, S.AREA_EXTENTS, S.VOXEL_SIZE)
+        keep = O.empty_anchor_filter_2d(a, occ, S.VOXEL_SIZE, vox["min_coord"][[0, 2]], 1)
+        assert 9300 <= int(keep.sum()) <= 15100
+        assert 1750 <= int(occ.sum()) <= 4000
