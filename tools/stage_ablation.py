@@ -7,6 +7,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if os.environ.get("ABL_DIAG"):       # the diagnostic library: DODT_* knobs read the environment
+    from dodt_b200 import _lib
+    _lib.use_diag_library()
 from dodt_b200 import synth  # noqa: E402
 from dodt_b200.frontend import FrontEnd, HostFrame  # noqa: E402
 
