@@ -681,7 +681,7 @@ def run_ours(args):
     launch_bytes = G * abytes["S4"]                 # 199.36 MB per pair x G pairs per launch
     achieved = launch_bytes / (corr_launch_us * 1e-6) / 1e9
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "corr_async_k1<2,4,0,8,2> (S4 correlation, %.0f%% of the step's "
+    roofline = {"bound": "hbm", "kernel": "corr_feed_k1<2,8,2> (S4 correlation, TMA-fed, %.0f%% of the step's "
                                           "algorithmic bytes)" % (100.0 * abytes["S4"] / abytes["total"]),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8tbs": achieved / 8000.0,

@@ -61,6 +61,9 @@ SIGNATURES = {
     "dodt_lidar_to_camera": (c_int, [c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_int32,
                                      c_int32, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
+    "dodt_lidar_to_camera_aligned": (c_int, [c_void_p, c_int64, POINTER(c_double), POINTER(c_double), c_void_p,
+                                             POINTER(c_double), POINTER(c_double), c_int32, c_int32, c_void_p,
+                                             c_int32, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dodt_bev_slices": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int64, POINTER(BevParams), c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                 c_void_p]),
@@ -88,7 +91,7 @@ SIGNATURES = {
                                             c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dodt_offset_to_anchor": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
     "dodt_rpn_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double),
-                                POINTER(c_double), c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+                                POINTER(c_double), c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dodt_emit_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
                                      c_void_p]),
@@ -118,8 +121,8 @@ SIGNATURES = {
     "dodt_anchor_filter_fused_workspace_bytes": (c_size_t, [c_int64]),
     "dodt_anchor_filter_fused": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_double, c_double, c_void_p, c_void_p, c_void_p,
-                                         c_void_p, POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                         c_void_p, POINTER(c_double), c_int32, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dodt_three_d_iou_matrix": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "dodt_nms_workspace_bytes": (c_size_t, [c_int64]),
     "dodt_nms_state_offset": (c_size_t, [c_int64]),
@@ -127,7 +130,7 @@ SIGNATURES = {
                          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
-DODT_FE_VERSION = 200   # include/dodt_fe.h
+DODT_FE_VERSION = 201   # include/dodt_fe.h
 
 _lib = None
 _diag = False

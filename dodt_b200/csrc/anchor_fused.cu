@@ -42,6 +42,7 @@ struct FusedArgs {
   const float *rpn_scores;                            // [n] (may be null)
   const float *rpn_offsets;                           // [n, 6] (may be null: no decode)
   double x_min, x_max, z_min, z_max;
+  int decode_f32;               // 1: the TF graph's float32 decode (anchor_math.cuh)
   unsigned char *keep;          // [n]
   int *kept_idx;                // [n]
   int *n_kept;                  // [1]
@@ -151,9 +152,16 @@ anchor_filter_fused(const FusedArgs g) {
       reinterpret_cast<float4 *>(g.k_img_boxes)[pos] = __ldg(reinterpret_cast<const float4 *>(g.anchor_img_boxes) + src);
     if (g.k_scores) g.k_scores[pos] = __ldg(g.rpn_scores + src);
     if (g.k_rpn_boxes) {
-      double r[6];
-      decode_anchor(g.anchors + src * 6, g.rpn_offsets + src * 6, r);
-      reinterpret_cast<float4 *>(g.k_rpn_boxes)[pos] = bev_box_of(r, g.x_min, g.x_max, g.z_min, g.z_max);
+      if (g.decode_f32) {
+        float r[6];
+        decode_anchor_f32(g.anchors + src * 6, g.rpn_offsets + src * 6, r);
+        reinterpret_cast<float4 *>(g.k_rpn_boxes)[pos] =
+            bev_box_of_f32(r, bev_extents_f32(g.x_min, g.x_max, g.z_min, g.z_max));
+      } else {
+        double r[6];
+        decode_anchor(g.anchors + src * 6, g.rpn_offsets + src * 6, r);
+        reinterpret_cast<float4 *>(g.k_rpn_boxes)[pos] = bev_box_of(r, g.x_min, g.x_max, g.z_min, g.z_max);
+      }
     }
   }
 
@@ -185,9 +193,9 @@ int dodt_anchor_filter_fused(const double *anchors, int64_t n, const int32_t *ii
                              int32_t band_rows, int32_t nx, int32_t nz, int32_t min_x, int32_t min_z,
                              double voxel_size, double density_threshold, const float *anchor_bev_boxes,
                              const float *anchor_img_boxes, const float *rpn_scores, const float *rpn_offsets,
-                             const double bev_extents[4], uint8_t *keep, int32_t *kept_idx, int32_t *n_kept,
-                             float *k_bev_boxes, float *k_img_boxes, float *k_scores, float *k_rpn_boxes,
-                             void *workspace, size_t workspace_bytes, dodt_stream_t stream_) {
+                             const double bev_extents[4], int32_t decode_f32, uint8_t *keep, int32_t *kept_idx,
+                             int32_t *n_kept, float *k_bev_boxes, float *k_img_boxes, float *k_scores,
+                             float *k_rpn_boxes, void *workspace, size_t workspace_bytes, dodt_stream_t stream_) {
   using namespace dodt;
   if (n < 0 || n > 0x7FFFFFFF || !ii || nx <= 0 || nz <= 0 || !(voxel_size > 0.0) || !n_kept) return DODT_EINVAL;
   if (bandoff && band_rows <= 0) return DODT_EINVAL;
@@ -215,6 +223,7 @@ int dodt_anchor_filter_fused(const double *anchors, int64_t n, const int32_t *ii
   g.rpn_scores = rpn_scores; g.rpn_offsets = rpn_offsets;
   g.x_min = bev_extents ? bev_extents[0] : 0.0; g.x_max = bev_extents ? bev_extents[1] : 1.0;
   g.z_min = bev_extents ? bev_extents[2] : 0.0; g.z_max = bev_extents ? bev_extents[3] : 1.0;
+  g.decode_f32 = decode_f32 ? 1 : 0;
   g.keep = keep; g.kept_idx = kept_idx; g.n_kept = n_kept;
   g.k_bev_boxes = k_bev_boxes; g.k_img_boxes = k_img_boxes; g.k_scores = k_scores; g.k_rpn_boxes = k_rpn_boxes;
   g.status = static_cast<unsigned long long *>(workspace);

@@ -143,7 +143,7 @@ rpn_decode_kernel(const double *__restrict__ anchors, const float *__restrict__ 
                   const int *__restrict__ idx, const int *__restrict__ idx2,
                   const int *__restrict__ count, int n_max,
                   double x_min, double x_max, double z_min, double z_max, const Calib P,
-                  double img_h, double img_w, float *__restrict__ bev_boxes,
+                  double img_h, double img_w, int decode_f32, float *__restrict__ bev_boxes,
                   float *__restrict__ img_boxes) {
   const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= n_max || i >= __ldg(count)) return;
@@ -151,10 +151,21 @@ rpn_decode_kernel(const double *__restrict__ anchors, const float *__restrict__ 
   const double *a = anchors + src * 6;
   const float *o = offsets + src * 6;
   double r[6];
-  decode_anchor(a, o, r);
+  if (decode_f32) {
+    // the TF graph's float32 chain; the image projection below (a float32 matmul in TF, whose
+    // summation order is cuBLAS's) continues in float64 from the float32 regressed anchor
+    float rf[6];
+    decode_anchor_f32(a, o, rf);
+    if (bev_boxes)
+      reinterpret_cast<float4 *>(bev_boxes)[i] = bev_box_of_f32(rf, bev_extents_f32(x_min, x_max, z_min, z_max));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) r[k] = rf[k];
+  } else {
+    decode_anchor(a, o, r);
+    if (bev_boxes)   // [z1, x1, z2, x2] normalised (project_to_bev + reorder_projected_boxes)
+      reinterpret_cast<float4 *>(bev_boxes)[i] = bev_box_of(r, x_min, x_max, z_min, z_max);
+  }
   const double hx = __ddiv_rn(r[3], 2.0), hz = __ddiv_rn(r[5], 2.0);
-  if (bev_boxes)   // [z1, x1, z2, x2] normalised (project_to_bev + reorder_projected_boxes)
-    reinterpret_cast<float4 *>(bev_boxes)[i] = bev_box_of(r, x_min, x_max, z_min, z_max);
   if (img_boxes) {   // [y1, x1, y2, x2] normalised (project_to_image_space + reorder)
     const double xs[2] = {__dadd_rn(r[0], hx), __dsub_rn(r[0], hx)};
     const double ys[2] = {r[1], __dsub_rn(r[1], r[4])};
@@ -309,8 +320,8 @@ int dodt_offset_to_anchor(const void *anchors, int32_t anchors_dtype, const void
 int dodt_rpn_decode(const double *anchors, const float *offsets, const int32_t *idx,
                     const int32_t *idx2, const int32_t *count, int64_t n_max,
                     const double bev_extents[4],
-                    const double p2[12], int32_t image_h, int32_t image_w, float *bev_boxes,
-                    float *img_boxes, dodt_stream_t stream_) {
+                    const double p2[12], int32_t image_h, int32_t image_w, int32_t decode_f32,
+                    float *bev_boxes, float *img_boxes, dodt_stream_t stream_) {
   using namespace dodt;
   if (n_max < 0 || n_max > 0x7FFFFFFF || !count || !bev_extents) return DODT_EINVAL;
   if (img_boxes && (!p2 || image_h <= 0 || image_w <= 0)) return DODT_EINVAL;
@@ -322,7 +333,7 @@ int dodt_rpn_decode(const double *anchors, const float *offsets, const int32_t *
   for (int k = 0; k < 12; ++k) P.p[k] = p2 ? p2[k] : 0.0;
   rpn_decode_kernel<<<ceil_div(n_max, 128), 128, 0, as_stream(stream_)>>>(
       anchors, offsets, idx, idx2, count, static_cast<int>(n_max), bev_extents[0], bev_extents[1],
-      bev_extents[2], bev_extents[3], P, image_h, image_w, bev_boxes, img_boxes);
+      bev_extents[2], bev_extents[3], P, image_h, image_w, decode_f32 ? 1 : 0, bev_boxes, img_boxes);
   DODT_AFTER_LAUNCH();
   return DODT_OK;
 }

@@ -4,6 +4,10 @@
 //   wavedata/wavedata/tools/core/calib_utils.py:394-410          project_to_image
 //   wavedata/wavedata/tools/obj_detection/tracking_utils.py:152-203  get_lidar_point_cloud
 //       (points with camera z > 0 whose projection lies strictly inside the image, input order)
+//   avod/datasets/kitti/kitti_tracking_dataset.py:317-328           point_cloud_transform: the scan of
+//       frame t+tau moved into frame t's LiDAR frame, (xyz + trans) @ matrix in float64, stored
+//       back into the float32 scan (dodt_lidar_to_camera_aligned; trans / matrix are the host OXTS
+//       arithmetic of kitti_tracking_utils.py:129-216)
 //
 // One pass computes the rectified camera coordinates (float64, as the reference: np.dot of float64
 // calibration matrices) and the keep flag of every point; the ordered compaction reuses the
@@ -20,16 +24,31 @@ struct LidarGeom {
   double m[12];   // rows 0..2 of R0_rect(4x4) . Tr_velo_to_cam(4x4)
   double p[12];   // camera matrix P2
   double im_w, im_h;
+  double et[3];   // ego-motion alignment: translation ...
+  double er[9];   // ... and 3x3 matrix (row-major), applied as (xyz + et) @ er
   int filter;     // 0: keep every point (im_size not given)
+  int ego;        // 1: align the scan first (the result is rounded to float32 like the reference's store)
 };
 
 __global__ void __launch_bounds__(256)
 lidar_transform(const float4 *__restrict__ velo, long long n, const LidarGeom g,
-                double *__restrict__ cam /* (3, n) */, unsigned char *__restrict__ keep) {
+                double *__restrict__ cam /* (3, n) */, unsigned char *__restrict__ keep,
+                float4 *__restrict__ aligned /* [n] or null */) {
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n) return;
   const float4 v = __ldg(velo + i);
-  const double x = v.x, y = v.y, z = v.z;
+  double x = v.x, y = v.y, z = v.z;
+  if (g.ego) {
+    // kitti_tracking_dataset.py:326: pc_next[:, :3] = (pc_next[:, :3] + trans) @ matrix — float64
+    // arithmetic assigned into the float32 scan
+    const double ax = __dadd_rn(x, g.et[0]), ay = __dadd_rn(y, g.et[1]), az = __dadd_rn(z, g.et[2]);
+    float al[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      al[j] = __double2float_rn(fma(az, g.er[6 + j], fma(ay, g.er[3 + j], __dmul_rn(ax, g.er[j]))));
+    x = al[0]; y = al[1]; z = al[2];
+    if (aligned) aligned[i] = make_float4(al[0], al[1], al[2], v.w);
+  }
   double c[3];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
@@ -80,7 +99,18 @@ int dodt_lidar_to_camera(const float *velo, int64_t n, const double rectified[12
                          const double p2[12], int32_t image_w, int32_t image_h, void *points,
                          int32_t points_dtype, int64_t row_stride, int32_t *count, void *workspace,
                          size_t workspace_bytes, dodt_stream_t stream_) {
+  return dodt_lidar_to_camera_aligned(velo, n, nullptr, nullptr, nullptr, rectified, p2, image_w, image_h, points,
+                                      points_dtype, row_stride, count, workspace, workspace_bytes, stream_);
+}
+
+int dodt_lidar_to_camera_aligned(const float *velo, int64_t n, const double ego_trans[3],
+                                 const double ego_matrix[9], float *aligned, const double rectified[12],
+                                 const double p2[12], int32_t image_w, int32_t image_h, void *points,
+                                 int32_t points_dtype, int64_t row_stride, int32_t *count, void *workspace,
+                                 size_t workspace_bytes, dodt_stream_t stream_) {
   using namespace dodt;
+  if ((ego_trans == nullptr) != (ego_matrix == nullptr) || (aligned && !ego_trans)) return DODT_EINVAL;
+  if (aligned && reinterpret_cast<uintptr_t>(aligned) % 16 != 0) return DODT_EALIGN;
   if (n < 0 || n > 0x7FFFFFFF || !rectified || !count || row_stride < n) return DODT_EINVAL;
   if (points_dtype != DODT_F32 && points_dtype != DODT_F64) return DODT_EINVAL;
   const bool filter = image_w > 0 && image_h > 0;
@@ -106,8 +136,12 @@ int dodt_lidar_to_camera(const float *velo, int64_t n, const double rectified[12
   LidarGeom g;
   for (int k = 0; k < 12; ++k) { g.m[k] = rectified[k]; g.p[k] = p2 ? p2[k] : 0.0; }
   g.im_w = image_w; g.im_h = image_h; g.filter = filter ? 1 : 0;
+  g.ego = ego_trans ? 1 : 0;
+  for (int k = 0; k < 3; ++k) g.et[k] = ego_trans ? ego_trans[k] : 0.0;
+  for (int k = 0; k < 9; ++k) g.er[k] = ego_matrix ? ego_matrix[k] : 0.0;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-  lidar_transform<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(velo), n, g, cam, keep);
+  lidar_transform<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(velo), n, g, cam, keep,
+                                              reinterpret_cast<float4 *>(aligned));
   DODT_AFTER_LAUNCH();
   const int rc = dodt_compact_mask(keep, n, idx, count, cws, workspace_bytes - off, stream_);
   if (rc != DODT_OK) return rc;

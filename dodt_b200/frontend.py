@@ -55,6 +55,10 @@ class FrontEndConfig:
                                                     # for the RPN NMS in a graph; a frame that needs more
                                                     # reports n_top[1] == 0 and is finished by
                                                     # FrontEnd.complete_frame
+    decode_tf_float32: bool = True                  # RPN decode + BEV projection as the reference's inference
+                                                    # graph computes them (float32 tf.Tensor branches,
+                                                    # dt_rpn_model.py:568-591); False: the float64 NumPy
+                                                    # branches of the same functions
     corr_pairs_per_launch: int = 8                  # consecutive pairs per frame-stream S4 launch
     corr_max_ctas: int = 0                          # CTA cap of the correlation launch (0 = none: two
                                                     # persistent CTAs per SM). 148 (one per SM, the other
@@ -320,7 +324,8 @@ class FrontEnd:
         # one launch: the BEV boxes come out of the same arithmetic as k_rpn_boxes (same bits as a
         # gather of the survivors' rows)
         ops.rpn_decode(self.anchors, s.rpn_offsets, s.kept_idx, s.n_top, self.bev_extents4,
-                       c.stereo_calib_p2, c.image_shape, s.prop_bev_boxes, s.prop_img_boxes, idx2=s.top_idx)
+                       c.stereo_calib_p2, c.image_shape, s.prop_bev_boxes, s.prop_img_boxes, idx2=s.top_idx,
+                       tf_float32=c.decode_tf_float32)
 
     # ---------------------------------------------------------------------------------------
     def rpn_nms_complete(self, frame):
@@ -365,7 +370,7 @@ class FrontEnd:
                                 anchor_img_boxes=self.anchor_img_boxes, k_img_boxes=s.k_img_boxes,
                                 rpn_scores=s.rpn_scores, k_scores=s.k_rpn_scores,
                                 rpn_offsets=s.rpn_offsets, bev_extents=self.bev_extents4,
-                                k_rpn_boxes=s.k_rpn_boxes)
+                                k_rpn_boxes=s.k_rpn_boxes, tf_float32=c.decode_tf_float32)
 
     def _enqueue_pre(self, s, skip):
         c = self.cfg

@@ -206,11 +206,11 @@ def anchor_filter_fused_workspace(n, device):
 def anchor_filter_fused(anchors, ii, nx, nz, min_x, min_z, voxel_size, density_threshold, keep, kept_idx,
                         n_kept, workspace, bandoff=None, band_rows=0, anchor_bev_boxes=None, k_bev_boxes=None,
                         anchor_img_boxes=None, k_img_boxes=None, rpn_scores=None, k_scores=None,
-                        rpn_offsets=None, bev_extents=None, k_rpn_boxes=None):
+                        rpn_offsets=None, bev_extents=None, k_rpn_boxes=None, tf_float32=False):
     """S2 of the frame stream in one launch: keep mask of the float64 anchors, ordered compaction
     (kept_idx, n_kept on the device) and, at the compacted positions, the anchors' crop boxes, RPN
     scores and decoded BEV boxes. ii is the full integral image, or the band-local one when
-    bandoff / band_rows (integral_image_2d_banded) are given."""
+    bandoff / band_rows (integral_image_2d_banded) are given. tf_float32: decode like rpn_decode."""
     _need_cuda(anchors, ii, bandoff, keep, kept_idx, n_kept, workspace, anchor_bev_boxes, k_bev_boxes,
                anchor_img_boxes, k_img_boxes, rpn_scores, k_scores, rpn_offsets, k_rpn_boxes)
     if anchors.dtype != torch.float64 or anchors.dim() != 2 or anchors.shape[1] != 6 or not anchors.is_contiguous():
@@ -219,7 +219,8 @@ def anchor_filter_fused(anchors, ii, nx, nz, min_x, min_z, voxel_size, density_t
     check(load().dodt_anchor_filter_fused(
         _ptr(anchors), n, _ptr(ii), _ptr(bandoff), int(band_rows), nx, nz, min_x, min_z, float(voxel_size),
         float(density_threshold), _ptr(anchor_bev_boxes), _ptr(anchor_img_boxes), _ptr(rpn_scores),
-        _ptr(rpn_offsets), _dbl(bev_extents, 4) if bev_extents is not None else None, _ptr(keep),
+        _ptr(rpn_offsets), _dbl(bev_extents, 4) if bev_extents is not None else None, int(bool(tf_float32)),
+        _ptr(keep),
         _ptr(kept_idx), _ptr(n_kept), _ptr(k_bev_boxes), _ptr(k_img_boxes), _ptr(k_scores), _ptr(k_rpn_boxes),
         _ptr(workspace), workspace.numel(), _stream()), "dodt_anchor_filter_fused")
 
@@ -279,12 +280,15 @@ def gather_rows_multi(pairs, idx, count):
 
 
 def lidar_to_camera(velo, rectified, p2=None, im_size=None, dtype=torch.float64, out=None,
-                    count=None, workspace=None):
+                    count=None, workspace=None, ego=None, aligned=None):
     """velo [n, 4] CUDA float32 (KITTI .bin rows) -> (points (3, n) of dtype with the first
     count[0] columns valid, count [1] int32), both on the device, no synchronisation.
     rectified: rows 0..2 of R0_rect(4x4).Tr_velo_to_cam(4x4); im_size = [w, h] enables the
-    image-frustum filter of wavedata tracking_utils.get_lidar_point_cloud."""
-    _need_cuda(velo, out, count, workspace)
+    image-frustum filter of wavedata tracking_utils.get_lidar_point_cloud.
+    ego = (trans[3], matrix[3, 3]): first move the scan into the previous frame's LiDAR frame,
+    float32((xyz + trans) @ matrix) (kitti_tracking_dataset.py:317-328); aligned: optional [n, 4]
+    float32 out tensor that receives the moved scan."""
+    _need_cuda(velo, out, count, workspace, aligned)
     if velo.dim() != 2 or velo.shape[1] != 4 or velo.dtype != torch.float32:
         raise ValueError("velo must be an [n, 4] float32 tensor (x, y, z, intensity)")
     velo = velo.contiguous()
@@ -296,11 +300,17 @@ def lidar_to_camera(velo, rectified, p2=None, im_size=None, dtype=torch.float64,
         count = torch.empty((1,), dtype=torch.int32, device=dev)
     if workspace is None:
         workspace = torch.empty(int(load().dodt_lidar_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    if aligned is not None and (ego is None or aligned.shape != velo.shape or aligned.dtype != torch.float32
+                                or not aligned.is_contiguous()):
+        raise ValueError("aligned must be a contiguous [n, 4] float32 tensor and needs ego")
     w, h = (int(im_size[0]), int(im_size[1])) if im_size is not None else (0, 0)
-    check(load().dodt_lidar_to_camera(_ptr(velo), n, _dbl(np.asarray(rectified)[:3], 12),
-                                      _dbl(p2, 12) if p2 is not None else None, w, h, _ptr(out),
-                                      _dtype_code(out), out.stride(0), _ptr(count), _ptr(workspace),
-                                      workspace.numel(), _stream()), "dodt_lidar_to_camera")
+    trans, matrix = (None, None) if ego is None else (_dbl(ego[0], 3), _dbl(ego[1], 9))
+    check(load().dodt_lidar_to_camera_aligned(_ptr(velo), n, trans, matrix,
+                                              _ptr(aligned) if aligned is not None else None,
+                                              _dbl(np.asarray(rectified)[:3], 12),
+                                              _dbl(p2, 12) if p2 is not None else None, w, h, _ptr(out),
+                                              _dtype_code(out), out.stride(0), _ptr(count), _ptr(workspace),
+                                              workspace.numel(), _stream()), "dodt_lidar_to_camera_aligned")
     return out, count
 
 
@@ -376,10 +386,11 @@ def offset_to_anchor(anchors, offsets):
 
 
 def rpn_decode(anchors, offsets, idx, count, bev_extents, stereo_calib_p2, image_shape, bev_boxes,
-               img_boxes, idx2=None):
+               img_boxes, idx2=None, tf_float32=False):
     """Regressed + projected boxes of the anchors idx[:count[0]] (device-side count), or of
     idx[idx2[:count[0]]]: bev_boxes [n_max, 4] [z1,x1,z2,x2], img_boxes [n_max, 4] [y1,x1,y2,x2],
-    float32, normalised; either may be None."""
+    float32, normalised; either may be None. tf_float32: the float32 tf.Tensor branches the
+    reference's inference graph runs (dt_rpn_model.py:568-591) instead of the float64 NumPy ones."""
     _need_cuda(anchors, offsets, idx, count, bev_boxes, img_boxes, idx2)
     if anchors.dtype != torch.float64 or offsets.dtype != torch.float32:
         raise TypeError("rpn_decode expects float64 anchors and float32 offsets")
@@ -388,7 +399,8 @@ def rpn_decode(anchors, offsets, idx, count, bev_extents, stereo_calib_p2, image
     n_max = (bev_boxes if bev_boxes is not None else img_boxes).shape[0]
     check(load().dodt_rpn_decode(_ptr(anchors), _ptr(offsets), _ptr(idx), _ptr(idx2), _ptr(count), n_max,
                                  _dbl(bev_extents, 4), _dbl(stereo_calib_p2, 12), int(image_shape[0]),
-                                 int(image_shape[1]), _ptr(bev_boxes), _ptr(img_boxes), _stream()),
+                                 int(image_shape[1]), int(bool(tf_float32)), _ptr(bev_boxes), _ptr(img_boxes),
+                                 _stream()),
           "dodt_rpn_decode")
 
 

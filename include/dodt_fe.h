@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DODT_FE_VERSION 200 /* major*100 + minor */
+#define DODT_FE_VERSION 201 /* major*100 + minor */
 
 typedef void *dodt_stream_t; /* cudaStream_t */
 
@@ -154,15 +154,15 @@ int dodt_integral_image_2d_banded(const uint8_t *occ, int32_t nx, int32_t nz, in
  * n_kept [1] (device), k_* [n,4] / [n] at the compacted positions (any of the k_* with its source
  * may be NULL). workspace: dodt_anchor_filter_fused_workspace_bytes(n), ZERO before its first use
  * (every call leaves it zero). Same results as dodt_anchor_filter_2d + dodt_compact_mask +
- * dodt_gather_rows_multi + dodt_rpn_decode. */
+ * dodt_gather_rows_multi + dodt_rpn_decode. decode_f32: as in dodt_rpn_decode. */
 size_t dodt_anchor_filter_fused_workspace_bytes(int64_t n);
 int dodt_anchor_filter_fused(const double *anchors, int64_t n, const int32_t *ii, const int32_t *bandoff,
                              int32_t band_rows, int32_t nx, int32_t nz, int32_t min_x, int32_t min_z,
                              double voxel_size, double density_threshold, const float *anchor_bev_boxes,
                              const float *anchor_img_boxes, const float *rpn_scores, const float *rpn_offsets,
-                             const double bev_extents[4], uint8_t *keep, int32_t *kept_idx, int32_t *n_kept,
-                             float *k_bev_boxes, float *k_img_boxes, float *k_scores, float *k_rpn_boxes,
-                             void *workspace, size_t workspace_bytes, dodt_stream_t stream);
+                             const double bev_extents[4], int32_t decode_f32, uint8_t *keep, int32_t *kept_idx,
+                             int32_t *n_kept, float *k_bev_boxes, float *k_img_boxes, float *k_scores,
+                             float *k_rpn_boxes, void *workspace, size_t workspace_bytes, dodt_stream_t stream);
 
 /* coords (n,2) [x,z] of dtype -> idx int32 (n,2); division in the coordinate dtype, truncation
  * toward zero, shift by the grid minimum, clip to [0, ndiv] (voxel_grid_2d.py:182-184) */
@@ -213,6 +213,19 @@ int dodt_lidar_to_camera(const float *velo, int64_t n, const double rectified[12
                          const double p2[12], int32_t image_w, int32_t image_h, void *points,
                          int32_t points_dtype, int64_t row_stride, int32_t *count, void *workspace,
                          size_t workspace_bytes, dodt_stream_t stream);
+/* The same with the ego-motion alignment of DODT's frame pairs in front of it
+ * (avod/datasets/kitti/kitti_tracking_dataset.py:317-328, point_cloud_transform): the scan of frame
+ * t+tau is moved into frame t's LiDAR frame, xyz <- float32((xyz + ego_trans) @ ego_matrix)
+ * (float64 arithmetic stored back into the float32 scan, as the reference's assignment does), then
+ * rectified / filtered as above. ego_trans[3], ego_matrix[9] (row-major 3x3): host, from the OXTS
+ * records (kitti_tracking_utils.py:189-207; dodt_b200.lidar.coordinate_transform); both NULL = no
+ * alignment. aligned: optional out, device float32 [n, 4] (moved x, y, z, intensity unchanged),
+ * 16-byte aligned, or NULL. */
+int dodt_lidar_to_camera_aligned(const float *velo, int64_t n, const double ego_trans[3],
+                                 const double ego_matrix[9], float *aligned, const double rectified[12],
+                                 const double p2[12], int32_t image_w, int32_t image_h, void *points,
+                                 int32_t points_dtype, int64_t row_stride, int32_t *count, void *workspace,
+                                 size_t workspace_bytes, dodt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Anchor geometry between the stages — host NumPy in the reference.
@@ -253,12 +266,17 @@ int dodt_offset_to_anchor(const void *anchors, int32_t anchors_dtype, const void
  * bev_boxes[i] = normalised BEV corners [z1, x1, z2, x2]; img_boxes[i] = normalised image corners
  * [y1, x1, y2, x2] (either output may be NULL). anchors [m, 6] float64, offsets [m, 6] float32.
  * idx2 (optional) selects among the kept anchors, e.g. the NMS survivors: the image projection
- * (eight corners in float64) is only needed for those. n_max bounds i. */
+ * (eight corners in float64) is only needed for those. n_max bounds i.
+ * decode_f32 = 0: the NumPy branches of offset_to_anchor / project_to_bev, float64 throughout,
+ * rounded to float32 at the end. 1: their tf.Tensor branches as the reference's inference graph runs
+ * them on float32 placeholders (dt_rpn_model.py:568-591): anchors rounded to float32, one float32
+ * operation per TF op, exp / log correctly rounded (TF's GPU expf / logf are within 2 ulp of that);
+ * the image projection continues in float64 from the float32 regressed anchor. */
 int dodt_rpn_decode(const double *anchors, const float *offsets, const int32_t *idx,
                     const int32_t *idx2, const int32_t *count, int64_t n_max,
                     const double bev_extents[4],
-                    const double p2[12], int32_t image_h, int32_t image_w, float *bev_boxes,
-                    float *img_boxes, dodt_stream_t stream);
+                    const double p2[12], int32_t image_h, int32_t image_w, int32_t decode_f32,
+                    float *bev_boxes, float *img_boxes, dodt_stream_t stream);
 
 /* Multi-GPU hand-off (the per-frame rows the reference writes with np.savetxt,
  * avod/core/dt_evaluator.py:1098-1147, and that a sharded run gathers once per shard): appends the

@@ -10,6 +10,7 @@ computes the same things on the device (dodt_b200/csrc/anchors.cu) and never imp
   project_to_bev          avod/core/anchor_projector.py:13-69
   project_to_image_space  avod/core/anchor_projector.py:72-156 (+ wavedata calib_utils.py:394-410)
   offset_to_anchor        avod/core/anchor_encoder.py:99-150
+  offset_to_anchor_tf32 / project_to_bev_tf32   the tf.Tensor branches of the two, float32 op by op
   reorder_projected_boxes avod/core/anchor_projector.py:254-273
 """
 import numpy as np
@@ -87,6 +88,45 @@ def offset_to_anchor(anchors, offsets):
     return np.stack((o[:, 0] * a[:, 3] + a[:, 0], o[:, 1] * a[:, 4] + a[:, 1],
                      o[:, 2] * a[:, 5] + a[:, 2], np.exp(np.log(a[:, 3]) + o[:, 3]),
                      np.exp(np.log(a[:, 4]) + o[:, 4]), np.exp(np.log(a[:, 5]) + o[:, 5])), axis=1)
+
+
+def _f32_exp(x):
+    """Correctly rounded float32 exp (evaluated in float64, rounded once)."""
+    return np.exp(x.astype(np.float64)).astype(np.float32)
+
+
+def _f32_log(x):
+    return np.log(x.astype(np.float64)).astype(np.float32)
+
+
+def offset_to_anchor_tf32(anchors, offsets):
+    """The tf.Tensor branch of offset_to_anchor (anchor_encoder.py:118-139) as the inference graph
+    runs it (dt_rpn_model.py:568-572): anchors and offsets are float32 tensors, every TF op is one
+    float32 operation. exp / log are correctly rounded here; TF's GPU kernels are within 2 ulp."""
+    a, o = np.asarray(anchors).astype(np.float32), np.asarray(offsets).astype(np.float32)
+    pos = [(o[:, k] * a[:, 3 + k]) + a[:, k] for k in range(3)]
+    dim = [_f32_exp(_f32_log(a[:, 3 + k]) + o[:, 3 + k]) for k in range(3)]
+    out = np.stack(pos + dim, axis=1)
+    assert out.dtype == np.float32
+    return out
+
+
+def project_to_bev_tf32(anchors, bev_extents):
+    """The tf.Tensor branch of project_to_bev (anchor_projector.py:13-69) on float32 anchors: the
+    extents are Python floats, so their differences are formed in float64 and enter the graph as
+    float32 constants. -> (corners, normalised corners) [x1, z1, x2, z2], float32."""
+    a = np.asarray(anchors)
+    assert a.dtype == np.float32
+    f = np.float32
+    x, z, hx, hz = a[:, 0], a[:, 2], a[:, 3] / f(2.0), a[:, 5] / f(2.0)
+    x_min, x_max = bev_extents[0][0], bev_extents[0][1]
+    z_min, z_max = bev_extents[1][0], bev_extents[1][1]
+    corners = np.stack([x - hx, f(z_max) - (z + hz), x + hx, f(z_max) - (z - hz)], axis=1)
+    corners = corners - np.array([x_min, z_min, x_min, z_min], dtype=f)
+    rng = np.array([x_max - x_min, z_max - z_min, x_max - x_min, z_max - z_min], dtype=f)
+    out = corners / rng
+    assert corners.dtype == f and out.dtype == f
+    return corners, out
 
 
 def reorder_projected_boxes(box_corners):

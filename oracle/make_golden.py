@@ -94,6 +94,37 @@ def lidar_frame():
     print("lidar", velo.shape, "->", np.asarray(fov).shape)
 
 
+def lidar_pair():
+    """DODT's frame pair ingest: the scan of frame t+1 moved into frame t's LiDAR frame with the OXTS
+    records (KittiTrackingDataset.coordinate_transform / point_cloud_transform, run unbound on a
+    stand-in that only has oxts_dir — the real constructor needs the protobuf configs), then the
+    frustum crop of KittiTrackingUtils.transfer_lidar_to_camera_view."""
+    import types
+    from wavedata.tools.core import calib_utils
+    from wavedata.tools.obj_detection import tracking_utils
+    from avod.datasets.kitti.kitti_tracking_dataset import KittiTrackingDataset
+    base = os.path.join(ref_shim.REFERENCE_ROOT, "avod/tests/datasets/Kitti/tracking/training")
+    names = ["000003", "000004"]
+    ds = types.SimpleNamespace(oxts_dir=base + "/oxts")
+    for m in ("get_oxts", "coordinate_transform", "point_cloud_transform"):
+        setattr(ds, m, types.MethodType(getattr(KittiTrackingDataset, m), ds))
+    trans, matrix, delta = ds.coordinate_transform(names)
+    raw = [tracking_utils.get_raw_lidar_point_cloud(n, base + "/velodyne") for n in names]
+    raw[1] = np.ascontiguousarray(raw[1][:, ::4])            # every 4th point keeps the fixture small
+    velo1 = raw[1].T.copy()
+    moved = ds.point_cloud_transform([raw[0], raw[1].copy()], names)[1]
+    assert moved.dtype == np.float32
+    fov = tracking_utils.get_lidar_in_camera_view(moved.copy(), names[1], base + "/calib", im_size=[1242, 375])
+    calib = calib_utils.read_tracking_calibration(base + "/calib", 0)
+    lines = [open(base + "/oxts/0000.txt").read().splitlines()[i] for i in (3, 4)]
+    oxts = np.array([[float(v) for v in ln.split()[:6]] for ln in lines])
+    np.savez_compressed(os.path.join(OUT, "lidar_pair_000003_000004.npz"), velo1=velo1, oxts=oxts,
+                        oxts_line0=lines[0], oxts_line1=lines[1], trans=trans, matrix=matrix, delta=delta,
+                        moved=np.asarray(moved), fov=np.asarray(fov), p2=calib.p2, r0_rect=calib.r0_rect,
+                        tr_velodyne_to_cam=calib.tr_velodyne_to_cam, im_size=np.array([1242, 375]))
+    print("lidar pair", velo1.shape, "trans", trans, "->", np.asarray(fov).shape)
+
+
 def synth_frame():
     pc = S.point_cloud(7, 0, n_points=30000).astype(np.float64)
     # make slice 4 degenerate (a single point) and put points exactly on slice boundaries
@@ -203,6 +234,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     kitti_frames()
     lidar_frame()
+    lidar_pair()
     synth_frame()
     unit_vectors()
     independent_tf_ops()

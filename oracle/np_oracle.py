@@ -6,6 +6,7 @@ computes for each stage, each function citing the reference file:line it follows
 to the Guoxs/DODT checkout):
 
   (ingest) lidar_to_cam_frame / lidar_in_camera_view   (wavedata calib_utils / tracking_utils)
+           oxts_coordinate_transform / point_cloud_transform (ego-motion alignment of DODT's frame pairs)
   S1  bev_slices / voxelize_2d / point_filter / dist_to_plane / density
   S2  integral_image_2d / map_to_index / empty_anchor_filter_2d
   S3  crop_and_resize       (TensorFlow 1.3.0 core/kernels/crop_and_resize_op.cc — NOT vendored
@@ -59,6 +60,36 @@ def lidar_in_camera_view(velo, r0_rect, tr_velodyne_to_cam, p2, im_size=None):
     u, v = uvw[0] / uvw[2], uvw[1] / uvw[2]
     keep = (u > 0) & (u < im_size[0]) & (v > 0) & (v < im_size[1])
     return pts[keep].T
+
+
+def oxts_coordinate_transform(cur, nxt):
+    """avod/datasets/kitti/kitti_tracking_dataset.py:300-315 (coordinate_transform) with the Oxts
+    arithmetic of kitti_tracking_utils.py:141-216. cur / nxt: the first six values of the two oxts
+    lines (latitude, longitude [deg], altitude, roll, pitch, yaw [rad]). Returns (trans [3],
+    matrix [3, 3], yaw difference)."""
+    lat1, lon1 = cur[0] * np.pi / 180.00, cur[1] * np.pi / 180.00
+    lat2, lon2 = nxt[0] * np.pi / 180.00, nxt[1] * np.pi / 180.00
+    a = lat2 - lat1
+    b = lon2 - lon1
+    d = abs(2 * 6378137.0 * np.arcsin(np.sqrt(np.power(np.sin(a / 2), 2) +
+                                               np.cos(lat1) * np.cos(lat2) * np.power(np.sin(b / 2), 2))))
+    d_roll, d_pitch, d_yaw = cur[3] - nxt[3], cur[4] - nxt[4], cur[5] - nxt[5]
+    trans = np.array([d * np.cos(d_yaw), d * np.sin(d_yaw), d * np.sin(d_pitch)])
+    c, s = np.cos(d_pitch), np.sin(d_pitch)
+    rz = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])       # "rotz": pitch difference, x-z plane
+    c, s = np.cos(d_roll), np.sin(d_roll)
+    rx = np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+    c, s = np.cos(d_yaw), np.sin(d_yaw)
+    ry = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])       # "roty": yaw difference, x-y plane
+    return trans, rz @ rx @ ry, d_yaw
+
+
+def point_cloud_transform(pc_next, trans, matrix):
+    """kitti_tracking_dataset.py:317-328: pc_next (4, N) float32 scan of frame t+tau (x, y, z,
+    intensity rows) -> the same array with xyz = float32((xyz + trans) @ matrix)."""
+    out = np.array(pc_next, dtype=np.float32).T.copy()
+    out[:, :3] = (out[:, :3] + trans) @ matrix              # float64 product stored as float32
+    return out.T
 
 
 # ------------------------------------------------------------------------------------------

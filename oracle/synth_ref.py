@@ -53,12 +53,20 @@ def anchor_set():
     return _ANCHOR_CACHE
 
 
-def decoded_boxes(offsets):
+def decoded_boxes(offsets, tf_float32=True):
     """rpn_boxes / rpn_img_boxes ([y1,x1,y2,x2] float32, all anchors) for float32 RPN offsets: the
-    reference's NumPy chain offset_to_anchor -> project_to_bev / project_to_image_space -> reorder."""
+    reference's chain offset_to_anchor -> project_to_bev / project_to_image_space -> reorder.
+    tf_float32 (the frame runner's default, FrontEndConfig.decode_tf_float32): the float32 tf.Tensor
+    branches the inference graph runs; False: the float64 NumPy branches. The image projection is
+    float64 from the regressed anchor either way (a float32 matmul in the TF graph)."""
     a, _, _ = anchor_set()
-    regressed = A.offset_to_anchor(a, np.asarray(offsets, dtype=np.float32).astype(np.float64))
-    _, bev_norm = A.project_to_bev(regressed, BEV_EXTENTS)
+    if tf_float32:
+        regressed = A.offset_to_anchor_tf32(a, np.asarray(offsets, dtype=np.float32))
+        _, bev_norm = A.project_to_bev_tf32(regressed, BEV_EXTENTS)
+        regressed = regressed.astype(np.float64)
+    else:
+        regressed = A.offset_to_anchor(a, np.asarray(offsets, dtype=np.float32).astype(np.float64))
+        _, bev_norm = A.project_to_bev(regressed, BEV_EXTENTS)
     _, img_norm = A.project_to_image_space(regressed, A.KITTI_P2, IMAGE_SHAPE)
     return dict(rpn_boxes=A.reorder_projected_boxes(bev_norm).astype(np.float32),
                 rpn_img_boxes=A.reorder_projected_boxes(img_norm).astype(np.float32))

@@ -60,7 +60,7 @@ def test_struct_layouts_match_header(lib, tmp_path):
 
 def test_host_only_entry_points(lib):
     from dodt_b200 import _lib, ops
-    assert lib.dodt_version() == 200
+    assert lib.dodt_version() == 201
     assert lib.dodt_strerror(0).decode().lower().startswith("ok") or lib.dodt_strerror(0)
     for code in (_lib.DODT_EINVAL, _lib.DODT_ESHAPE, _lib.DODT_ECAPACITY, _lib.DODT_ECUDA, _lib.DODT_EALIGN):
         assert len(lib.dodt_strerror(code)) > 0

@@ -99,3 +99,41 @@ def test_rpn_decode_chain_matches_host(ops):
     np.testing.assert_allclose(dev_boxes.cpu().numpy(), bev_norm, rtol=1e-6, atol=1e-7)
     keep = dd.non_max_suppression(dev_boxes, torch.from_numpy(scores).cuda(), 300, 0.8).cpu().numpy()
     np.testing.assert_array_equal(keep, O.non_max_suppression(dev_boxes.cpu().numpy(), scores, 300, 0.8))
+
+
+def test_rpn_decode_tf_float32_branch(ops):
+    """decode_f32: the tf.Tensor branches the reference's inference graph runs on float32 placeholders
+    (dt_rpn_model.py:568-591), op by op in float32 with correctly rounded exp / log == the float32
+    restatement in oracle/anchor_helpers.py, bit for bit (a float64 exp / log result within 1e-16 of
+    a float32 tie could round the other way: not observed); the float64 NumPy branch differs from it
+    by a few float32 ulps, which is why the runner follows the graph."""
+    import dodt_b200 as dd
+    from oracle import np_oracle as O
+    a = S.car_anchors()
+    rng = np.random.default_rng(21)
+    off = rng.normal(0.0, 0.1, (len(a), 6)).astype(np.float32)
+    reg = A.offset_to_anchor_tf32(a, off)
+    _, bev = A.project_to_bev_tf32(reg, S.BEV_EXTENTS)
+    want_bev = A.reorder_projected_boxes(bev)
+    _, img = A.project_to_image_space(reg.astype(np.float64), A.KITTI_P2, S.IMAGE_SHAPE)
+    want_img = A.reorder_projected_boxes(img)
+    n = len(a)
+    idx = torch.arange(n, dtype=torch.int32, device="cuda")
+    cnt = torch.tensor([n], dtype=torch.int32, device="cuda")
+    got_bev = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    got_img = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    t_a, t_off = torch.from_numpy(a).cuda(), torch.from_numpy(off).cuda()
+    ops.rpn_decode(t_a, t_off, idx, cnt, [-40, 40, 0, 70], A.KITTI_P2.reshape(-1), S.IMAGE_SHAPE, got_bev, got_img,
+                   tf_float32=True)
+    np.testing.assert_array_equal(got_bev.cpu().numpy(), want_bev)
+    np.testing.assert_allclose(got_img.cpu().numpy(), want_img, rtol=1e-6, atol=1e-7)
+    f64_bev = torch.empty_like(got_bev)
+    ops.rpn_decode(t_a, t_off, idx, cnt, [-40, 40, 0, 70], A.KITTI_P2.reshape(-1), S.IMAGE_SHAPE, f64_bev, None)
+    diff = (f64_bev != got_bev).float().mean().item()
+    assert 0.0 < diff < 0.9                                   # the two branches are different roundings
+    np.testing.assert_allclose(f64_bev.cpu().numpy(), want_bev, rtol=2e-5, atol=2e-6)
+    # NMS on the graph's boxes: the device picks what the oracle picks on the oracle's boxes
+    scores = rng.permutation(np.linspace(0.01, 0.99, n)).astype(np.float32)
+    sub = slice(0, n, 7)
+    keep = dd.non_max_suppression(got_bev[sub], torch.from_numpy(scores[sub]).cuda(), 1024, 0.8).cpu().numpy()
+    np.testing.assert_array_equal(keep, O.non_max_suppression(want_bev[sub], scores[sub], 1024, 0.8))

@@ -88,6 +88,16 @@ def test_fused_filter_equals_unfused_chain_and_oracle(n_anchors, seed):
     ops.rpn_decode(t_anchors, offsets, idx2, cnt2, [-40, 40, 0, 70], synth.A.KITTI_P2.reshape(-1), synth.IMAGE_SHAPE,
                    want_rpn, None)
     assert torch.equal(k_rpn[:len(idx)], want_rpn[:len(idx)])
+    # the float32 tf.Tensor-branch decode (the frame runner's default) through both entry points
+    ops.rpn_decode(t_anchors, offsets, idx2, cnt2, [-40, 40, 0, 70], synth.A.KITTI_P2.reshape(-1), synth.IMAGE_SHAPE,
+                   want_rpn, None, tf_float32=True)
+    ops.anchor_filter_fused(t_anchors, ii_local, nx, nz, min_x, min_z, voxel, thr, keep, kept_idx, n_kept, ws,
+                            bandoff=bandoff, band_rows=band_rows, rpn_offsets=offsets, bev_extents=[-40, 40, 0, 70],
+                            k_rpn_boxes=k_rpn, tf_float32=True)
+    assert torch.equal(k_rpn[:len(idx)], want_rpn[:len(idx)])
+    reg = synth.A.offset_to_anchor_tf32(anchors[idx], offsets.cpu().numpy()[idx])
+    np.testing.assert_array_equal(k_rpn[:len(idx)].cpu().numpy(),
+                                  synth.A.reorder_projected_boxes(synth.A.project_to_bev_tf32(reg, synth.BEV_EXTENTS)[1]))
     # ... and with the FULL image handed to the fused kernel (bandoff = None)
     keep.fill_(9)
     ops.anchor_filter_fused(t_anchors, ii, nx, nz, min_x, min_z, voxel, thr, keep, kept_idx, n_kept, ws)

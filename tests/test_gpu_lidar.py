@@ -54,6 +54,42 @@ def test_lidar_edge_cases(frame):
         ops.lidar_to_camera(torch.zeros(4, 4), np.eye(4))
 
 
+def test_ego_motion_alignment_equals_reference(lib):
+    """The frame-pair ingest: frame t+1's scan moved into frame t's LiDAR frame (OXTS records), then
+    rectified and frustum-cropped, in one pass on the device == the outputs of the reference's
+    point_cloud_transform + get_lidar_in_camera_view frozen in tests/golden/. The moved scan is
+    float32((xyz + trans) @ matrix); np's matmul order is BLAS-defined, so a value may round the other
+    way when its float64 result lies within 1e-16 of a float32 tie: at most 1 float32 ulp, almost never."""
+    from dodt_b200 import lidar
+    g = np.load(os.path.join(GOLDEN, "lidar_pair_000003_000004.npz"))
+    calib = SimpleNamespace(r0_rect=g["r0_rect"], tr_velodyne_to_cam=g["tr_velodyne_to_cam"], p2=g["p2"])
+    trans, matrix, _ = lidar.coordinate_transform(str(g["oxts_line0"]), str(g["oxts_line1"]))
+    moved = lidar.point_cloud_transform(g["velo1"].T, trans, matrix)
+    assert moved.dtype == np.float32 and moved.shape == g["moved"].shape
+    assert (moved != g["moved"]).mean() < 1e-5
+    np.testing.assert_allclose(moved, g["moved"], rtol=1.2e-7, atol=0)
+    np.testing.assert_array_equal(lidar.point_cloud_transform(g["velo1"].T[:3], trans, matrix), moved[:3])
+    fov = lidar.get_lidar_in_camera_view(g["velo1"], calib, im_size=list(g["im_size"]), ego=(trans, matrix))
+    assert fov.shape == g["fov"].shape
+    if np.array_equal(moved, g["moved"]):
+        np.testing.assert_allclose(fov, g["fov"], rtol=1e-12, atol=1e-12)
+    else:
+        np.testing.assert_allclose(fov, g["fov"], rtol=1e-6, atol=1e-5)
+    # device-resident: the count stays on the GPU, the points feed dodt_bev_slices(n_dev) directly
+    pts, count = lidar.get_lidar_in_camera_view(torch.from_numpy(g["velo1"]).cuda(), calib,
+                                                im_size=list(g["im_size"]), ego=(trans, matrix))
+    assert int(count.item()) == g["fov"].shape[1]
+    np.testing.assert_array_equal(pts[:, :int(count.item())].cpu().numpy(), fov)
+    # against the oracle on other inputs
+    rng = np.random.default_rng(5)
+    velo = rng.uniform(-70, 70, (4000, 4)).astype(np.float32)
+    t2, m2, _ = O.oxts_coordinate_transform([49.0, 8.4, 115, 0.01, -0.02, 1.0], [49.00001, 8.40002, 115, 0.02, -0.01, 0.97])
+    want = O.point_cloud_transform(velo.T, t2, m2)
+    got = lidar.point_cloud_transform(velo.T, t2, m2)
+    np.testing.assert_allclose(got, want, rtol=1.2e-7, atol=0)
+    assert (got != want).mean() < 1e-3
+
+
 def test_ingest_to_bev_on_device(frame):
     """Raw scan -> frustum cloud -> six BEV maps + anchor keep mask with the point count staying on
     the device (dodt_bev_slices n_dev): equal to the reference's outputs for that frame."""

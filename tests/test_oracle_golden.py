@@ -319,6 +319,27 @@ def test_lidar_ingest_against_reference_outputs():
     np.testing.assert_array_equal(g["fov"], _load("s1s2_kitti_000003.npz")["points"])
 
 
+def test_ego_motion_alignment_against_reference_outputs():
+    """DODT's frame-pair ingest (KittiTrackingDataset.coordinate_transform / point_cloud_transform run
+    from the checkout on fixture frames 000003 -> 000004, frozen by oracle/make_golden.py): the OXTS
+    scalars and the moved float32 scan are reproduced bit for bit by the oracle and by the host
+    mirror of the product package; the frustum crop of the moved scan keeps the same points."""
+    from dodt_b200 import lidar
+    g = _load("lidar_pair_000003_000004.npz")
+    for trans, matrix, delta in (O.oxts_coordinate_transform(g["oxts"][0], g["oxts"][1]),
+                                 lidar.coordinate_transform(str(g["oxts_line0"]), str(g["oxts_line1"]))):
+        np.testing.assert_array_equal(trans, g["trans"])
+        np.testing.assert_array_equal(matrix, g["matrix"])
+        assert delta == g["delta"]
+    moved = O.point_cloud_transform(g["velo1"].T, g["trans"], g["matrix"])
+    assert moved.dtype == np.float32
+    np.testing.assert_array_equal(moved, g["moved"])
+    np.testing.assert_array_equal(moved[3], g["velo1"][:, 3])          # intensity untouched
+    fov = O.lidar_in_camera_view(moved.T, g["r0_rect"], g["tr_velodyne_to_cam"], g["p2"], list(g["im_size"]))
+    assert fov.shape == g["fov"].shape == (3, 5443)
+    np.testing.assert_allclose(fov, g["fov"], rtol=1e-13, atol=1e-13)
+
+
 def test_kitti_like_cloud_has_the_surveyed_occupancy():
     """synth.point_cloud_kitti (bench.py --workload kitti) lands in the ranges SURVEY 8(d) measured on
     the reference's real KITTI tracking frames: 16-20 k points, 9.3-15.1 k of 89 600 anchors kept by

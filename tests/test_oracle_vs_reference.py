@@ -128,3 +128,28 @@ def test_anchor_helpers_live():
     # [y1, x1, y2, x2] <- [x1, y1, x2, y2]; it cannot run without TensorFlow
     b = np.random.default_rng(4).random((9, 4))
     np.testing.assert_array_equal(A.reorder_projected_boxes(b), b[:, [1, 0, 3, 2]])
+
+
+def test_oxts_alignment_live():
+    """Oxts arithmetic and point_cloud_transform of the checkout on random records / scans == the
+    oracle restatement and the product's host mirror (needs the whole checkout, not the staged S1/S2)."""
+    if not ref_shim.full_checkout():
+        pytest.skip("needs avod.datasets of the full checkout")
+    import types
+    from avod.datasets.kitti.kitti_tracking_utils import Oxts
+    from avod.datasets.kitti.kitti_tracking_dataset import KittiTrackingDataset
+    from dodt_b200 import lidar
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        rec = np.concatenate([[49.0 + rng.normal(0, 1e-4), 8.4 + rng.normal(0, 1e-4), 115.0], rng.normal(0, 0.05, 3)])
+        nxt = rec + np.concatenate([rng.normal(0, 1e-5, 2), [0.0], rng.normal(0, 0.01, 3)])
+        lines = [" ".join(repr(float(v)) for v in np.concatenate([r, np.zeros(24)])) for r in (rec, nxt)]
+        ds = types.SimpleNamespace(get_oxts=lambda name: Oxts(lines[int(name)]))
+        ds.coordinate_transform = types.MethodType(KittiTrackingDataset.coordinate_transform, ds)
+        want = ds.coordinate_transform(["0", "1"])
+        for got in (O.oxts_coordinate_transform(rec, nxt), lidar.coordinate_transform(lines[0], lines[1])):
+            for a, b in zip(got, want):
+                np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
+        pc = rng.uniform(-60, 60, (4, 500)).astype(np.float32)
+        moved = types.MethodType(KittiTrackingDataset.point_cloud_transform, ds)([pc.copy(), pc.copy()], ["0", "1"])[1]
+        np.testing.assert_array_equal(O.point_cloud_transform(pc, want[0], want[1]), moved)
