@@ -90,6 +90,32 @@ def test_ego_motion_alignment_equals_reference(lib):
     assert (got != want).mean() < 1e-3
 
 
+def test_file_level_drop_ins_equal_reference(frame, tmp_path):
+    """wavedata's tracking_utils.get_lidar_point_cloud / get_lidar_in_camera_view and the frame-pair
+    ingest of KittiTrackingDataset.load_samples, called by file name like the reference, on a KITTI
+    directory rebuilt from the committed fixtures == the reference's frozen outputs."""
+    from dodt_b200 import tracking_utils as T
+    g, _ = frame
+    gp = np.load(os.path.join(GOLDEN, "lidar_pair_000003_000004.npz"))
+    mini = os.path.join(GOLDEN, "kitti_mini")
+    velo_dir = str(tmp_path / "velodyne")
+    os.makedirs(velo_dir + "/0000")
+    g["velo"].tofile(velo_dir + "/0000/000003.bin")
+    gp["velo1"].tofile(velo_dir + "/0000/000004.bin")
+    fov = T.get_lidar_point_cloud("000003", mini + "/calib", velo_dir, im_size=[1242, 375])
+    assert fov.shape == g["fov"].shape and fov.dtype == np.float64
+    np.testing.assert_allclose(fov, g["fov"], rtol=1e-12, atol=1e-12)
+    full = T.get_lidar_point_cloud("000003", mini + "/calib", velo_dir)
+    np.testing.assert_allclose(full[:, ::7], g["full_every_7th"], rtol=1e-12, atol=1e-12)
+    pair = T.get_pair_point_clouds(["000003", "000004"], mini + "/calib", velo_dir, mini + "/oxts",
+                                   [(375, 1242), (375, 1242)])
+    np.testing.assert_allclose(pair[0], g["fov"], rtol=1e-12, atol=1e-12)
+    assert pair[1].shape == gp["fov"].shape
+    np.testing.assert_allclose(pair[1], gp["fov"], rtol=1e-6, atol=1e-5)
+    with pytest.raises(ValueError):
+        T.get_lidar_point_cloud("000003", mini + "/calib", velo_dir, im_size=[1242, 375], min_intensity=0.1)
+
+
 def test_ingest_to_bev_on_device(frame):
     """Raw scan -> frustum cloud -> six BEV maps + anchor keep mask with the point count staying on
     the device (dodt_bev_slices n_dev): equal to the reference's outputs for that frame."""

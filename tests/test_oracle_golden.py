@@ -340,6 +340,30 @@ def test_ego_motion_alignment_against_reference_outputs():
     np.testing.assert_allclose(fov, g["fov"], rtol=1e-13, atol=1e-13)
 
 
+def test_tracking_file_readers_against_reference_outputs(tmp_path):
+    """dodt_b200.tracking_utils' host-side readers (KITTI calibration text, oxts line, velodyne .bin)
+    on the reference's fixture files (tests/golden/kitti_mini: calib/0000.txt and the first six oxts
+    lines, data files of the KITTI tracking set) == what the reference's readers returned when
+    oracle/make_golden.py ran them."""
+    from dodt_b200 import tracking_utils as T
+    mini = os.path.join(GOLDEN, "kitti_mini")
+    g, gp = _load("lidar_kitti_000003.npz"), _load("lidar_pair_000003_000004.npz")
+    calib = T.read_tracking_calibration(mini + "/calib", 0)
+    for k in ("p2", "r0_rect", "tr_velodyne_to_cam"):
+        np.testing.assert_array_equal(getattr(calib, k), g[k])
+    assert calib.p0.shape == calib.p1.shape == calib.p3.shape == (3, 4)
+    for i, frame in enumerate(("000003", "000004")):
+        rec = T.get_oxts(mini + "/oxts", frame)
+        np.testing.assert_array_equal([rec.latitude, rec.longitude, rec.altitude, rec.roll, rec.pitch, rec.yaw],
+                                      gp["oxts"][i])
+    os.makedirs(tmp_path / "velodyne" / "0000")
+    g["velo"].tofile(tmp_path / "velodyne" / "0000" / "000003.bin")
+    raw = T.get_raw_lidar_point_cloud("000003", str(tmp_path / "velodyne"))
+    assert raw.dtype == np.float32 and raw.shape == (4, len(g["velo"]))
+    np.testing.assert_array_equal(raw.T, g["velo"])
+    assert T.read_lidar(str(tmp_path / "velodyne" / "0000"), 99) == []
+
+
 def test_kitti_like_cloud_has_the_surveyed_occupancy():
     """synth.point_cloud_kitti (bench.py --workload kitti) lands in the ranges SURVEY 8(d) measured on
     the reference's real KITTI tracking frames: 16-20 k points, 9.3-15.1 k of 89 600 anchors kept by

@@ -3,6 +3,8 @@ Python is imported from the read-only checkout through oracle/ref_shim.py and ru
 inputs next to the restatement. Skipped where the checkout does not exist (the GPU box); the frozen
 outputs under tests/golden/ (tests/test_oracle_golden.py) cover that case.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -153,3 +155,26 @@ def test_oxts_alignment_live():
         pc = rng.uniform(-60, 60, (4, 500)).astype(np.float32)
         moved = types.MethodType(KittiTrackingDataset.point_cloud_transform, ds)([pc.copy(), pc.copy()], ["0", "1"])[1]
         np.testing.assert_array_equal(O.point_cloud_transform(pc, want[0], want[1]), moved)
+
+
+def test_tracking_file_readers_live():
+    """The product's calibration / oxts / velodyne readers == the reference's on its own fixtures."""
+    if not ref_shim.full_checkout():
+        pytest.skip("needs the fixture data of the full checkout")
+    from wavedata.tools.core import calib_utils
+    from wavedata.tools.obj_detection import tracking_utils
+    from avod.datasets.kitti.kitti_tracking_utils import Oxts
+    from dodt_b200 import tracking_utils as T
+    base = os.path.join(ref_shim.REFERENCE_ROOT, "avod/tests/datasets/Kitti/tracking/training")
+    for video in (0, 1):
+        want, got = calib_utils.read_tracking_calibration(base + "/calib", video), \
+            T.read_tracking_calibration(base + "/calib", video)
+        for k in ("p0", "p1", "p2", "p3", "r0_rect", "tr_velodyne_to_cam"):
+            np.testing.assert_array_equal(getattr(got, k), getattr(want, k))
+    for name in ("000000", "000007", "010003"):
+        np.testing.assert_array_equal(T.get_raw_lidar_point_cloud(name, base + "/velodyne"),
+                                      tracking_utils.get_raw_lidar_point_cloud(name, base + "/velodyne"))
+        line = open(base + "/oxts/%04d.txt" % int(name[:2])).read().splitlines()[int(name[2:])]
+        a, b = T.get_oxts(base + "/oxts", name), Oxts(line)
+        assert (a.latitude, a.longitude, a.altitude, a.roll, a.pitch, a.yaw) == \
+            (b.latitude, b.longitude, b.altitude, b.roll, b.pitch, b.yaw)
