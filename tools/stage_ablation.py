@@ -21,6 +21,8 @@ if os.environ.get("ABL_CORR_CTAS"):
     cfg.corr_max_ctas = int(os.environ["ABL_CORR_CTAS"])
 if os.environ.get("ABL_NMS_WINDOWS"):
     cfg.nms_max_windows = int(os.environ["ABL_NMS_WINDOWS"])
+if os.environ.get("ABL_PRIO"):        # "chain,corr" stream priorities, e.g. -1,0
+    cfg.chain_stream_priority, cfg.corr_stream_priority = (int(v) for v in os.environ["ABL_PRIO"].split(","))
 fe = FrontEnd(cfg)
 slots = [fe.new_slot() for _ in range(n_slots)]
 for i, s in enumerate(slots):
