@@ -38,6 +38,12 @@ class BevParams(Structure):
     ]
 
 
+class AnchorGrid(Structure):
+    """struct dodt_anchor_grid."""
+    _fields_ = [("extents", c_double * 6), ("stride", c_double * 2), ("plane", c_double * 4),
+                ("sizes", c_double * 48), ("n_sizes", c_int32), ("reserved", c_int32)]
+
+
 class GatherSpec(Structure):
     """struct dodt_gather_spec."""
     _fields_ = [("src", c_void_p), ("dst", c_void_p), ("width", c_int32), ("reserved", c_int32)]
@@ -119,7 +125,7 @@ SIGNATURES = {
     "dodt_integral_image_2d_banded": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
                                               POINTER(c_void_p), c_void_p]),
     "dodt_anchor_filter_fused_workspace_bytes": (c_size_t, [c_int64]),
-    "dodt_anchor_filter_fused": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+    "dodt_anchor_filter_fused": (c_int, [c_void_p, POINTER(AnchorGrid), c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                          c_int32, c_int32, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                          c_void_p, POINTER(c_double), c_int32, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -14,6 +14,8 @@
 // then the tile's kept anchors are processed with dense lanes: kept index, the two precomputed
 // crop boxes, the RPN score and the decoded BEV box of the regressed anchor, all written at the
 // compacted position. The last tile writes the kept count and re-arms the workspace.
+#include <string.h>
+
 #include "anchor_math.cuh"
 #include "common.cuh"
 
@@ -30,7 +32,8 @@ __device__ __forceinline__ int clip_index(int trunc, int min_coord, int ndiv) {
 }
 
 struct FusedArgs {
-  const double *anchors;        // [n, 6]
+  const double *anchors;        // [n, 6], or null: the anchors are the grid `grid`, evaluated from the index
+  GridGeom grid;
   long long n;
   const int *ii;                // (nx+1) x (nz+1): full integral image, or band-local (bandoff != null)
   const int *bandoff;           // [bands, nz] exclusive band offsets, or null
@@ -75,8 +78,14 @@ anchor_filter_fused(const FusedArgs g) {
   // ---- keep flag (anchor_filter.py:93-119): corners in float64, stored to float32, map_to_index
   bool keep = false;
   if (i < g.n) {
-    const double *a = g.anchors + i * 6;
-    const double x = __ldg(a), z = __ldg(a + 2), hx = __ddiv_rn(__ldg(a + 3), 2.0), hz = __ddiv_rn(__ldg(a + 5), 2.0);
+    double a[6];
+    if (g.anchors) {
+      a[0] = __ldg(g.anchors + i * 6); a[2] = __ldg(g.anchors + i * 6 + 2);
+      a[3] = __ldg(g.anchors + i * 6 + 3); a[5] = __ldg(g.anchors + i * 6 + 5);
+    } else {
+      grid_anchor(g.grid, i, a);
+    }
+    const double x = a[0], z = a[2], hx = __ddiv_rn(a[3], 2.0), hz = __ddiv_rn(a[5], 2.0);
     const float tlx = __double2float_rn(__dsub_rn(x, hx)), tlz = __double2float_rn(__dsub_rn(z, hz));
     const float brx = __double2float_rn(__dadd_rn(x, hx)), brz = __double2float_rn(__dadd_rn(z, hz));
     const int x1 = clip_index(trunc_index_f32(tlx, g.voxel_f), g.min_x, g.nx);
@@ -152,14 +161,16 @@ anchor_filter_fused(const FusedArgs g) {
       reinterpret_cast<float4 *>(g.k_img_boxes)[pos] = __ldg(reinterpret_cast<const float4 *>(g.anchor_img_boxes) + src);
     if (g.k_scores) g.k_scores[pos] = __ldg(g.rpn_scores + src);
     if (g.k_rpn_boxes) {
+      double a[6];
+      if (g.anchors) load_anchor(g.anchors + src * 6, a); else grid_anchor(g.grid, src, a);
       if (g.decode_f32) {
         float r[6];
-        decode_anchor_f32(g.anchors + src * 6, g.rpn_offsets + src * 6, r);
+        decode_anchor_f32(a, g.rpn_offsets + src * 6, r);
         reinterpret_cast<float4 *>(g.k_rpn_boxes)[pos] =
             bev_box_of_f32(r, bev_extents_f32(g.x_min, g.x_max, g.z_min, g.z_max));
       } else {
         double r[6];
-        decode_anchor(g.anchors + src * 6, g.rpn_offsets + src * 6, r);
+        decode_anchor(a, g.rpn_offsets + src * 6, r);
         reinterpret_cast<float4 *>(g.k_rpn_boxes)[pos] = bev_box_of(r, g.x_min, g.x_max, g.z_min, g.z_max);
       }
     }
@@ -189,7 +200,8 @@ size_t dodt_anchor_filter_fused_workspace_bytes(int64_t n) {
   return (tiles + 2) * sizeof(unsigned long long);
 }
 
-int dodt_anchor_filter_fused(const double *anchors, int64_t n, const int32_t *ii, const int32_t *bandoff,
+int dodt_anchor_filter_fused(const double *anchors, const dodt_anchor_grid *grid, int64_t n, const int32_t *ii,
+                             const int32_t *bandoff,
                              int32_t band_rows, int32_t nx, int32_t nz, int32_t min_x, int32_t min_z,
                              double voxel_size, double density_threshold, const float *anchor_bev_boxes,
                              const float *anchor_img_boxes, const float *rpn_scores, const float *rpn_offsets,
@@ -204,7 +216,14 @@ int dodt_anchor_filter_fused(const double *anchors, int64_t n, const int32_t *ii
     DODT_CUDA_TRY(cudaMemsetAsync(n_kept, 0, sizeof(int32_t), stream));
     return DODT_OK;
   }
-  if (!anchors || !keep || !kept_idx) return DODT_EINVAL;
+  if ((!anchors && !grid) || !keep || !kept_idx) return DODT_EINVAL;
+  FusedArgs g;
+  memset(&g.grid, 0, sizeof(g.grid));
+  if (!anchors) {   // anchors as a function of the index
+    const int rc = fill_grid_geom(grid->extents, grid->sizes, grid->n_sizes, grid->stride, grid->plane, &g.grid);
+    if (rc != DODT_OK) return rc;
+    if (static_cast<int64_t>(g.grid.nx) * g.grid.nz * g.grid.n_sizes * 2 != n) return DODT_ESHAPE;
+  }
   if ((k_bev_boxes && !anchor_bev_boxes) || (k_img_boxes && !anchor_img_boxes) || (k_scores && !rpn_scores) ||
       (k_rpn_boxes && (!rpn_offsets || !bev_extents)))
     return DODT_EINVAL;
@@ -214,7 +233,6 @@ int dodt_anchor_filter_fused(const double *anchors, int64_t n, const int32_t *ii
   if (al % 16 != 0 || reinterpret_cast<uintptr_t>(workspace) % 8 != 0) return DODT_EALIGN;
   if (!workspace || workspace_bytes < dodt_anchor_filter_fused_workspace_bytes(n)) return DODT_ECAPACITY;
   const int tiles = ceil_div(n, kFuseBlock);
-  FusedArgs g;
   g.anchors = anchors; g.n = n; g.ii = ii; g.bandoff = bandoff; g.band_rows = band_rows;
   g.nx = nx; g.nz = nz; g.min_x = min_x; g.min_z = min_z;
   g.voxel_f = static_cast<float>(voxel_size);

@@ -15,14 +15,46 @@
 
 namespace dodt {
 
-// regressed anchor r[6] = offset_to_anchor(anchor a[6], offsets o[6])
-__device__ __forceinline__ void decode_anchor(const double *__restrict__ a, const float *__restrict__ o,
-                                              double r[6]) {
+// The anchor grid of avod/core/anchor_generators/grid_anchor_3d_generator.py:39-108 (tile_anchors_3d)
+// + box_3d_encoder.py:85-132 (box_3d_to_anchor) as a function of the anchor index: what
+// grid_anchors_kernel writes out and what the fused S2 kernel evaluates in place of a table read.
+constexpr int kMaxSizes = 16;
+struct GridGeom {
+  double x_start, x_delta, z_start, z_delta;   // centres: float32(start + i * delta), as np.arange fills
+  double a, b, c, d;                           // ground plane
+  double dims[kMaxSizes * 2][3];               // [size * 2 + rotation] -> dim_x, dim_y, dim_z
+  int nx, nz, n_sizes;
+};
+// host: fills g from the arguments of dodt_grid_anchors (defined in anchors.cu); DODT_OK or DODT_EINVAL
+int fill_grid_geom(const double ext[6], const double *sizes, int n_sizes, const double stride[2],
+                   const double plane[4], GridGeom *g);
+
+__device__ __forceinline__ void grid_anchor(const GridGeom &g, long long i, double a[6]) {
+  // meshgrid(x, z, size, rotation) with 'xy' indexing, reshaped row-major: z slowest, then x,
+  // then size, then rotation (grid_anchor_3d_generator.py:80-85)
+  const int combo = static_cast<int>(i % (2 * g.n_sizes));
+  const long long cell = i / (2 * g.n_sizes);
+  const int xi = static_cast<int>(cell % g.nx);
+  const int zi = static_cast<int>(cell / g.nx);
+  a[0] = static_cast<double>(__double2float_rn(__dadd_rn(g.x_start, __dmul_rn(static_cast<double>(xi), g.x_delta))));
+  a[2] = static_cast<double>(__double2float_rn(__dadd_rn(g.z_start, __dmul_rn(static_cast<double>(zi), g.z_delta))));
+  // all_y = -(a * all_x + c * all_z + d) / b
+  a[1] = __ddiv_rn(-__dadd_rn(__dadd_rn(__dmul_rn(g.a, a[0]), __dmul_rn(g.c, a[2])), g.d), g.b);
+  a[3] = g.dims[combo][0]; a[4] = g.dims[combo][1]; a[5] = g.dims[combo][2];
+}
+
+__device__ __forceinline__ void load_anchor(const double *__restrict__ p, double a[6]) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) a[k] = __ldg(p + k);
+}
+
+// regressed anchor r[6] = offset_to_anchor(anchor a[6] (values), offsets o[6] (device memory))
+__device__ __forceinline__ void decode_anchor(const double a[6], const float *__restrict__ o, double r[6]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     // x = dx * dim_x + x_anchor ; dim = exp(log(dim) + d)
-    r[k] = __dadd_rn(__dmul_rn(static_cast<double>(__ldg(o + k)), __ldg(a + 3 + k)), __ldg(a + k));
-    r[3 + k] = exp(__dadd_rn(log(__ldg(a + 3 + k)), static_cast<double>(__ldg(o + 3 + k))));
+    r[k] = __dadd_rn(__dmul_rn(static_cast<double>(__ldg(o + k)), a[3 + k]), a[k]);
+    r[3 + k] = exp(__dadd_rn(log(a[3 + k]), static_cast<double>(__ldg(o + 3 + k))));
   }
 }
 
@@ -41,11 +73,10 @@ __device__ __forceinline__ float4 bev_box_of(const double r[6], double x_min, do
 __device__ __forceinline__ float exp_f32(float x) { return __double2float_rn(exp(static_cast<double>(x))); }
 __device__ __forceinline__ float log_f32(float x) { return __double2float_rn(log(static_cast<double>(x))); }
 
-__device__ __forceinline__ void decode_anchor_f32(const double *__restrict__ a, const float *__restrict__ o,
-                                                  float r[6]) {
+__device__ __forceinline__ void decode_anchor_f32(const double a[6], const float *__restrict__ o, float r[6]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const float pos = __double2float_rn(__ldg(a + k)), dim = __double2float_rn(__ldg(a + 3 + k));
+    const float pos = __double2float_rn(a[k]), dim = __double2float_rn(a[3 + k]);
     r[k] = __fadd_rn(__fmul_rn(__ldg(o + k), dim), pos);
     r[3 + k] = exp_f32(__fadd_rn(log_f32(dim), __ldg(o + 3 + k)));
   }

@@ -25,32 +25,15 @@
 namespace dodt {
 namespace {
 
-constexpr int kMaxSizes = 16;
-
-struct GridGeom {
-  double x_start, x_delta, z_start, z_delta;   // centres: float32(start + i * delta), as np.arange fills
-  double a, b, c, d;                           // ground plane
-  double dims[kMaxSizes * 2][3];               // [size * 2 + rotation] -> dim_x, dim_y, dim_z
-  int nx, nz, n_sizes;
-};
-
 __global__ void __launch_bounds__(256)
 grid_anchors_kernel(const GridGeom g, long long n, double *__restrict__ anchors) {
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n) return;
-  // meshgrid(x, z, size, rotation) with 'xy' indexing, reshaped row-major: z slowest, then x,
-  // then size, then rotation (grid_anchor_3d_generator.py:80-85)
-  const int combo = static_cast<int>(i % (2 * g.n_sizes));
-  const long long cell = i / (2 * g.n_sizes);
-  const int xi = static_cast<int>(cell % g.nx);
-  const int zi = static_cast<int>(cell / g.nx);
-  const double x = static_cast<double>(__double2float_rn(__dadd_rn(g.x_start, __dmul_rn(static_cast<double>(xi), g.x_delta))));
-  const double z = static_cast<double>(__double2float_rn(__dadd_rn(g.z_start, __dmul_rn(static_cast<double>(zi), g.z_delta))));
-  // all_y = -(a * all_x + c * all_z + d) / b
-  const double y = __ddiv_rn(-__dadd_rn(__dadd_rn(__dmul_rn(g.a, x), __dmul_rn(g.c, z)), g.d), g.b);
+  double a[6];
+  grid_anchor(g, i, a);
   double *o = anchors + i * 6;
-  o[0] = x; o[1] = y; o[2] = z;
-  o[3] = g.dims[combo][0]; o[4] = g.dims[combo][1]; o[5] = g.dims[combo][2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) o[k] = a[k];
 }
 
 template <typename T>
@@ -148,7 +131,8 @@ rpn_decode_kernel(const double *__restrict__ anchors, const float *__restrict__ 
   const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= n_max || i >= __ldg(count)) return;
   const size_t src = static_cast<size_t>(__ldg(idx + (idx2 ? __ldg(idx2 + i) : i)));
-  const double *a = anchors + src * 6;
+  double a[6];
+  load_anchor(anchors + src * 6, a);
   const float *o = offsets + src * 6;
   double r[6];
   if (decode_f32) {
@@ -210,6 +194,27 @@ int fill_grid(const double ext[6], const double stride[2], int n_sizes, GridGeom
 }
 
 }  // namespace
+
+int fill_grid_geom(const double ext[6], const double *sizes, int n_sizes, const double stride[2],
+                   const double plane[4], GridGeom *g) {
+  const int rc = fill_grid(ext, stride, n_sizes, g);
+  if (rc != DODT_OK) return rc;
+  if (!sizes || !plane || plane[1] == 0.0) return DODT_EINVAL;
+  g->a = plane[0]; g->b = plane[1]; g->c = plane[2]; g->d = plane[3];
+  const double rot[2] = {0.0, M_PI / 2.0};
+  for (int s = 0; s < n_sizes; ++s)
+    for (int r = 0; r < 2; ++r) {
+      // box_3d_encoder.py:120-130: dim_x = l*|cos| + w*|sin|, dim_y = h, dim_z = w*|cos| + l*|sin|
+      volatile double cr = fabs(cos(rot[r])), sr = fabs(sin(rot[r]));
+      const double l = sizes[3 * s], w = sizes[3 * s + 1], h = sizes[3 * s + 2];
+      volatile double lc = l * cr, ws = w * sr, wc = w * cr, ls = l * sr;
+      g->dims[2 * s + r][0] = lc + ws;
+      g->dims[2 * s + r][1] = h;
+      g->dims[2 * s + r][2] = wc + ls;
+    }
+  return DODT_OK;
+}
+
 }  // namespace dodt
 
 extern "C" {
@@ -230,21 +235,8 @@ int dodt_grid_anchors(const double extents[6], const double *sizes, int32_t n_si
                       dodt_stream_t stream_) {
   using namespace dodt;
   GridGeom g;
-  const int rc = fill_grid(extents, stride, n_sizes, &g);
+  const int rc = fill_grid_geom(extents, sizes, n_sizes, stride, plane, &g);
   if (rc != DODT_OK) return rc;
-  if (!sizes || !plane || plane[1] == 0.0) return DODT_EINVAL;
-  g.a = plane[0]; g.b = plane[1]; g.c = plane[2]; g.d = plane[3];
-  const double rot[2] = {0.0, M_PI / 2.0};
-  for (int s = 0; s < n_sizes; ++s)
-    for (int r = 0; r < 2; ++r) {
-      // box_3d_encoder.py:120-130: dim_x = l*|cos| + w*|sin|, dim_y = h, dim_z = w*|cos| + l*|sin|
-      volatile double cr = fabs(cos(rot[r])), sr = fabs(sin(rot[r]));
-      const double l = sizes[3 * s], w = sizes[3 * s + 1], h = sizes[3 * s + 2];
-      volatile double lc = l * cr, ws = w * sr, wc = w * cr, ls = l * sr;
-      g.dims[2 * s + r][0] = lc + ws;
-      g.dims[2 * s + r][1] = h;
-      g.dims[2 * s + r][2] = wc + ls;
-    }
   const long long n = static_cast<long long>(g.nx) * g.nz * n_sizes * 2;
   if (n == 0) return DODT_OK;
   if (!anchors) return DODT_EINVAL;

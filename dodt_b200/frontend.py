@@ -225,6 +225,10 @@ class FrontEnd:
             else torch.device(device)
         self.nx, _, self.nz, self.min_x, _, self.min_z = ops.bev_grid(c.area_extents, c.voxel_size)
         with torch.cuda.device(self.device):
+            # S2 evaluates the config's anchor grid from the anchor index (no table read); a caller's own
+            # anchors are read from their table
+            self.anchor_grid = None if anchors is not None else \
+                (c.area_extents, c.anchor_3d_sizes, c.anchor_stride, c.ground_plane)
             if anchors is None:
                 # the anchor grid of the config, generated on the device (bit-identical to
                 # box_3d_to_anchor(tile_anchors_3d(...)))
@@ -373,14 +377,15 @@ class FrontEnd:
         # of the kept anchors (dt_rpn_model.py:573-591: regressed anchors projected into the BEV
         # map) in one kernel
         bandoff, band_rows = ops.integral_image_2d_banded(s.occ, s.ii, s.ws_ii)
-        ops.anchor_filter_fused(self.anchors, s.ii, self.nx, self.nz, self.min_x, self.min_z,
+        ops.anchor_filter_fused(None if self.anchor_grid is not None else self.anchors, s.ii, self.nx, self.nz,
+                                self.min_x, self.min_z,
                                 c.voxel_size, c.density_threshold, s.keep, s.kept_idx, s.n_kept,
                                 s.ws_fused, bandoff=bandoff, band_rows=band_rows,
                                 anchor_bev_boxes=self.anchor_bev_boxes, k_bev_boxes=s.k_bev_boxes,
                                 anchor_img_boxes=self.anchor_img_boxes, k_img_boxes=s.k_img_boxes,
                                 rpn_scores=s.rpn_scores, k_scores=s.k_rpn_scores,
                                 rpn_offsets=s.rpn_offsets, bev_extents=self.bev_extents4,
-                                k_rpn_boxes=s.k_rpn_boxes, tf_float32=c.decode_tf_float32)
+                                k_rpn_boxes=s.k_rpn_boxes, tf_float32=c.decode_tf_float32, grid=self.anchor_grid)
 
     def _enqueue_pre(self, s, skip):
         c = self.cfg

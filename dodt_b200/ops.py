@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (BEV_STATS_LEN, DODT_F32, DODT_F64, MAX_DENSITY_LUT, MAX_SLICES, BevParams,
+from ._lib import (BEV_STATS_LEN, DODT_F32, DODT_F64, MAX_DENSITY_LUT, MAX_SLICES, AnchorGrid, BevParams,
                    check, load)
 
 
@@ -206,18 +206,36 @@ def anchor_filter_fused_workspace(n, device):
 def anchor_filter_fused(anchors, ii, nx, nz, min_x, min_z, voxel_size, density_threshold, keep, kept_idx,
                         n_kept, workspace, bandoff=None, band_rows=0, anchor_bev_boxes=None, k_bev_boxes=None,
                         anchor_img_boxes=None, k_img_boxes=None, rpn_scores=None, k_scores=None,
-                        rpn_offsets=None, bev_extents=None, k_rpn_boxes=None, tf_float32=False):
+                        rpn_offsets=None, bev_extents=None, k_rpn_boxes=None, tf_float32=False, grid=None):
     """S2 of the frame stream in one launch: keep mask of the float64 anchors, ordered compaction
     (kept_idx, n_kept on the device) and, at the compacted positions, the anchors' crop boxes, RPN
     scores and decoded BEV boxes. ii is the full integral image, or the band-local one when
-    bandoff / band_rows (integral_image_2d_banded) are given. tf_float32: decode like rpn_decode."""
+    bandoff / band_rows (integral_image_2d_banded) are given. tf_float32: decode like rpn_decode.
+    grid = (area_extents, anchor_3d_sizes, anchor_stride, ground_plane) with anchors=None: the anchors
+    are that grid (grid_anchors) and are evaluated from the index inside the kernel, not read."""
     _need_cuda(anchors, ii, bandoff, keep, kept_idx, n_kept, workspace, anchor_bev_boxes, k_bev_boxes,
                anchor_img_boxes, k_img_boxes, rpn_scores, k_scores, rpn_offsets, k_rpn_boxes)
-    if anchors.dtype != torch.float64 or anchors.dim() != 2 or anchors.shape[1] != 6 or not anchors.is_contiguous():
-        raise TypeError("anchor_filter_fused expects contiguous float64 anchors (n, 6)")
-    n = anchors.shape[0]
+    grid_arg = None
+    if anchors is None:
+        if grid is None:
+            raise ValueError("anchor_filter_fused needs anchors or grid")
+        ext, sizes, stride, plane = grid
+        sizes = np.asarray(sizes, dtype=np.float64).reshape(-1, 3)
+        ga = AnchorGrid()
+        ga.extents[:] = [float(v) for v in np.asarray(ext, dtype=np.float64).reshape(-1)]
+        ga.stride[:] = [float(v) for v in stride]
+        ga.plane[:] = [float(v) for v in plane]
+        for i, v in enumerate(sizes.reshape(-1)):
+            ga.sizes[i] = float(v)
+        ga.n_sizes = len(sizes)
+        grid_arg = ctypes.byref(ga)
+        n = keep.shape[0]
+    else:
+        if anchors.dtype != torch.float64 or anchors.dim() != 2 or anchors.shape[1] != 6 or not anchors.is_contiguous():
+            raise TypeError("anchor_filter_fused expects contiguous float64 anchors (n, 6)")
+        n = anchors.shape[0]
     check(load().dodt_anchor_filter_fused(
-        _ptr(anchors), n, _ptr(ii), _ptr(bandoff), int(band_rows), nx, nz, min_x, min_z, float(voxel_size),
+        _ptr(anchors), grid_arg, n, _ptr(ii), _ptr(bandoff), int(band_rows), nx, nz, min_x, min_z, float(voxel_size),
         float(density_threshold), _ptr(anchor_bev_boxes), _ptr(anchor_img_boxes), _ptr(rpn_scores),
         _ptr(rpn_offsets), _dbl(bev_extents, 4) if bev_extents is not None else None, int(bool(tf_float32)),
         _ptr(keep),

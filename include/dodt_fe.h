@@ -155,8 +155,20 @@ int dodt_integral_image_2d_banded(const uint8_t *occ, int32_t nx, int32_t nz, in
  * may be NULL). workspace: dodt_anchor_filter_fused_workspace_bytes(n), ZERO before its first use
  * (every call leaves it zero). Same results as dodt_anchor_filter_2d + dodt_compact_mask +
  * dodt_gather_rows_multi + dodt_rpn_decode. decode_f32: as in dodt_rpn_decode. */
+/* anchors = NULL with grid != NULL: the anchors are the grid of dodt_grid_anchors(grid->...) and are
+ * evaluated from the anchor index inside the kernel instead of being read ("anchors
+ * become a function of index"); n must be the size of that grid. Same bits as with the table. */
+typedef struct dodt_anchor_grid {
+  double extents[6];      /* x_min, x_max, y_min, y_max, z_min, z_max                              */
+  double stride[2];       /* x, z                                                                   */
+  double plane[4];        /* a, b, c, d with b != 0                                                 */
+  double sizes[16 * 3];   /* n_sizes rows (l, w, h)                                                 */
+  int32_t n_sizes;        /* 1..16                                                                  */
+  int32_t reserved;
+} dodt_anchor_grid;
 size_t dodt_anchor_filter_fused_workspace_bytes(int64_t n);
-int dodt_anchor_filter_fused(const double *anchors, int64_t n, const int32_t *ii, const int32_t *bandoff,
+int dodt_anchor_filter_fused(const double *anchors, const dodt_anchor_grid *grid /* host */, int64_t n,
+                             const int32_t *ii, const int32_t *bandoff,
                              int32_t band_rows, int32_t nx, int32_t nz, int32_t min_x, int32_t min_z,
                              double voxel_size, double density_threshold, const float *anchor_bev_boxes,
                              const float *anchor_img_boxes, const float *rpn_scores, const float *rpn_offsets,

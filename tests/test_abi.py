@@ -41,20 +41,22 @@ def test_header_is_plain_c(tmp_path):
 
 
 def test_struct_layouts_match_header(lib, tmp_path):
-    """sizeof/offsetof of the three ABI structs as gcc sees the header == the ctypes mirrors."""
+    """sizeof/offsetof of the ABI structs as gcc sees the header == the ctypes mirrors."""
     from dodt_b200 import _lib
     src = tmp_path / "s.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dodt_fe.h"\nint main(void){'
-                   'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dodt_bev_params), '
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dodt_bev_params), '
                    'offsetof(dodt_bev_params, occ_lo), offsetof(dodt_bev_params, density_lut), '
                    'sizeof(dodt_gather_spec), offsetof(dodt_gather_spec, width), '
-                   'sizeof(dodt_crop_spec), offsetof(dodt_crop_spec, channels)); return 0; }\n')
+                   'sizeof(dodt_crop_spec), offsetof(dodt_crop_spec, channels), sizeof(dodt_anchor_grid), '
+                   'offsetof(dodt_anchor_grid, sizes), offsetof(dodt_anchor_grid, n_sizes)); return 0; }\n')
     exe = tmp_path / "s"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [ctypes.sizeof(_lib.BevParams), _lib.BevParams.occ_lo.offset, _lib.BevParams.density_lut.offset,
             ctypes.sizeof(_lib.GatherSpec), _lib.GatherSpec.width.offset,
-            ctypes.sizeof(_lib.CropSpec), _lib.CropSpec.channels.offset]
+            ctypes.sizeof(_lib.CropSpec), _lib.CropSpec.channels.offset,
+            ctypes.sizeof(_lib.AnchorGrid), _lib.AnchorGrid.sizes.offset, _lib.AnchorGrid.n_sizes.offset]
     assert got == want
 
 

@@ -95,6 +95,29 @@ def test_fused_filter_equals_unfused_chain_and_oracle(n_anchors, seed):
                             bandoff=bandoff, band_rows=band_rows, rpn_offsets=offsets, bev_extents=[-40, 40, 0, 70],
                             k_rpn_boxes=k_rpn, tf_float32=True)
     assert torch.equal(k_rpn[:len(idx)], want_rpn[:len(idx)])
+    if n_anchors == 89600:
+        # the anchors as a function of the index (no table read): same keep mask, order and decoded boxes
+        keep_g, kept_g, n_g, k_g = torch.empty_like(keep), torch.empty_like(kept_idx), torch.empty_like(n_kept), \
+            torch.empty_like(k_rpn)
+        for f32 in (True, False):
+            ops.anchor_filter_fused(None, ii_local, nx, nz, min_x, min_z, voxel, thr, keep_g, kept_g, n_g, ws,
+                                    bandoff=bandoff, band_rows=band_rows, rpn_offsets=offsets,
+                                    bev_extents=[-40, 40, 0, 70], k_rpn_boxes=k_g, tf_float32=f32,
+                                    grid=(synth.AREA_EXTENTS, synth.A.CAR_ANCHOR_SIZES, synth.ANCHOR_STRIDE,
+                                          synth.GROUND_PLANE))
+            ops.anchor_filter_fused(t_anchors, ii_local, nx, nz, min_x, min_z, voxel, thr, keep, kept_idx, n_kept, ws,
+                                    bandoff=bandoff, band_rows=band_rows, rpn_offsets=offsets,
+                                    bev_extents=[-40, 40, 0, 70], k_rpn_boxes=k_rpn, tf_float32=f32)
+            assert torch.equal(keep_g, keep) and torch.equal(n_g, n_kept)
+            assert torch.equal(kept_g[:len(idx)], kept_idx[:len(idx)]) and torch.equal(k_g[:len(idx)], k_rpn[:len(idx)])
+        with pytest.raises(Exception):     # a grid of another size than n
+            ops.anchor_filter_fused(None, ii_local, nx, nz, min_x, min_z, voxel, thr, keep_g[:1000], kept_g, n_g, ws,
+                                    bandoff=bandoff, band_rows=band_rows,
+                                    grid=(synth.AREA_EXTENTS, synth.A.CAR_ANCHOR_SIZES, synth.ANCHOR_STRIDE,
+                                          synth.GROUND_PLANE))
+        ops.anchor_filter_fused(t_anchors, ii_local, nx, nz, min_x, min_z, voxel, thr, keep, kept_idx, n_kept, ws,
+                                bandoff=bandoff, band_rows=band_rows, rpn_offsets=offsets, bev_extents=[-40, 40, 0, 70],
+                                k_rpn_boxes=k_rpn, tf_float32=True)
     reg = synth.A.offset_to_anchor_tf32(anchors[idx], offsets.cpu().numpy()[idx])
     np.testing.assert_array_equal(k_rpn[:len(idx)].cpu().numpy(),
                                   synth.A.reorder_projected_boxes(synth.A.project_to_bev_tf32(reg, synth.BEV_EXTENTS)[1]))
