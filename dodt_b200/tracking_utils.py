@@ -6,6 +6,7 @@ on-disk formats either side of it), same names and call signatures as the refere
   get_raw_lidar_point_cloud(name, velo_dir)          wavedata/.../obj_detection/tracking_utils.py:108-114
   get_lidar_in_camera_view(pts, name, calib_dir, im_size=None, min_intensity=None)      :115-148
   get_lidar_point_cloud(name, calib_dir, velo_dir, im_size=None, min_intensity=None)    :152-203
+  get_road_plane(name, planes_dir)                   :205-248 (host; DODT fixes the plane)
   get_oxts(oxts_dir, sample_name)                    avod/datasets/kitti/kitti_tracking_dataset.py:215-223
   get_pair_point_clouds(sample_names, ...)           kitti_tracking_dataset.py:485-494 (load_samples):
                                                      raw scans -> frame t+tau moved into frame t's LiDAR
@@ -82,6 +83,23 @@ def get_lidar_point_cloud(name, calib_dir, velo_dir, im_size=None, min_intensity
     (3, M) float64 like the reference."""
     return get_lidar_in_camera_view(get_raw_lidar_point_cloud(name, velo_dir), name, calib_dir,
                                     im_size=im_size, min_intensity=min_intensity)
+
+
+def get_road_plane(name, planes_dir):
+    """Ground plane (a, b, c, d) of a frame. The reference parses the 4th line of the frame's plane
+    file when it exists and then OVERRIDES the result for the tracking data sets with the fixed plane
+    [0, -1, 0, 1.65] (tracking_utils.py:232-236), normal facing up (+y is down), normalised: that
+    fixed plane is what every caller gets, whatever the file holds. A malformed existing file still
+    raises like the reference's parse does."""
+    video_id, frame_id = _ids(name)
+    plane_file = planes_dir + '/%04d/%06d.txt' % (video_id, frame_id)
+    if os.path.exists(plane_file):
+        with open(plane_file, 'r') as f:
+            [float(v) for v in f.readlines()[3].split()]
+    plane = np.asarray([0, -1, 0, 1.65])
+    if plane[1] > 0:
+        plane = -plane
+    return plane / np.linalg.norm(plane[0:3])
 
 
 def get_oxts(oxts_dir, sample_name):

@@ -362,6 +362,7 @@ def test_tracking_file_readers_against_reference_outputs(tmp_path):
     assert raw.dtype == np.float32 and raw.shape == (4, len(g["velo"]))
     np.testing.assert_array_equal(raw.T, g["velo"])
     assert T.read_lidar(str(tmp_path / "velodyne" / "0000"), 99) == []
+    np.testing.assert_array_equal(T.get_road_plane("000003", str(tmp_path / "planes")), [0.0, -1.0, 0.0, 1.65])
 
 
 def test_kitti_like_cloud_has_the_surveyed_occupancy():

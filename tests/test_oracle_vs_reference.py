@@ -178,3 +178,5 @@ def test_tracking_file_readers_live():
         a, b = T.get_oxts(base + "/oxts", name), Oxts(line)
         assert (a.latitude, a.longitude, a.altitude, a.roll, a.pitch, a.yaw) == \
             (b.latitude, b.longitude, b.altitude, b.roll, b.pitch, b.yaw)
+        np.testing.assert_array_equal(T.get_road_plane(name, base + "/planes"),
+                                      tracking_utils.get_road_plane(name, base + "/planes"))
