@@ -15,6 +15,8 @@
 // np.dot's summation order / FMA use is BLAS-defined, so coordinates agree with NumPy to float64
 // rounding noise (the keep decision could differ only for a point whose projection is within that
 // noise of the image border).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace dodt {
@@ -71,6 +73,21 @@ lidar_transform(const float4 *__restrict__ velo, long long n, const LidarGeom g,
   keep[i] = k ? 1 : 0;
 }
 
+// point_cloud_transform on its own (no rectification wanted): the moved scan only
+__global__ void __launch_bounds__(256)
+lidar_align(const float4 *__restrict__ velo, long long n, const LidarGeom g, float4 *__restrict__ aligned) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = __ldg(velo + i);
+  const double ax = __dadd_rn(static_cast<double>(v.x), g.et[0]), ay = __dadd_rn(static_cast<double>(v.y), g.et[1]),
+               az = __dadd_rn(static_cast<double>(v.z), g.et[2]);
+  float al[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    al[j] = __double2float_rn(fma(az, g.er[6 + j], fma(ay, g.er[3 + j], __dmul_rn(ax, g.er[j]))));
+  aligned[i] = make_float4(al[0], al[1], al[2], v.w);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 lidar_gather(const double *__restrict__ cam, long long n, const int *__restrict__ idx,
@@ -111,6 +128,20 @@ int dodt_lidar_to_camera_aligned(const float *velo, int64_t n, const double ego_
   using namespace dodt;
   if ((ego_trans == nullptr) != (ego_matrix == nullptr) || (aligned && !ego_trans)) return DODT_EINVAL;
   if (aligned && reinterpret_cast<uintptr_t>(aligned) % 16 != 0) return DODT_EALIGN;
+  if (aligned && !points) {
+    // alignment only: aligned <- the moved scan; rectified / p2 / points / count / workspace are not used
+    if (n < 0 || n > 0x7FFFFFFF || (n > 0 && !velo)) return DODT_EINVAL;
+    if (reinterpret_cast<uintptr_t>(velo) % 16 != 0) return DODT_EALIGN;
+    if (n == 0) return DODT_OK;
+    LidarGeom ga;
+    memset(&ga, 0, sizeof(ga));
+    for (int k = 0; k < 3; ++k) ga.et[k] = ego_trans[k];
+    for (int k = 0; k < 9; ++k) ga.er[k] = ego_matrix[k];
+    lidar_align<<<static_cast<unsigned>((n + 255) / 256), 256, 0, as_stream(stream_)>>>(
+        reinterpret_cast<const float4 *>(velo), n, ga, reinterpret_cast<float4 *>(aligned));
+    DODT_AFTER_LAUNCH();
+    return DODT_OK;
+  }
   if (n < 0 || n > 0x7FFFFFFF || !rectified || !count || row_stride < n) return DODT_EINVAL;
   if (points_dtype != DODT_F32 && points_dtype != DODT_F64) return DODT_EINVAL;
   const bool filter = image_w > 0 && image_h > 0;

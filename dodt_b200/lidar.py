@@ -101,8 +101,7 @@ def point_cloud_transform(point_cloud, trans, matrix):
     if pc.dim() != 2 or pc.shape[0] not in (3, 4):
         raise ValueError("expected a (3, N) or (4, N) point cloud, got {}".format(tuple(pc.shape)))
     velo, _ = _velo_tensor(pc.t())
-    aligned = torch.empty_like(velo)
-    ops.lidar_to_camera(velo, np.eye(4), ego=(trans, matrix), aligned=aligned, dtype=torch.float32)
+    aligned = ops.lidar_align(velo, trans, matrix)
     out = aligned[:, :pc.shape[0]].t().contiguous()
     return out.cpu().numpy() if was_numpy else out
 

@@ -332,6 +332,21 @@ def lidar_to_camera(velo, rectified, p2=None, im_size=None, dtype=torch.float64,
     return out, count
 
 
+def lidar_align(velo, trans, matrix, aligned=None):
+    """velo [n, 4] CUDA float32 -> the scan moved into the previous frame's LiDAR frame,
+    float32((xyz + trans) @ matrix), intensity unchanged (kitti_tracking_dataset.py:317-328)."""
+    _need_cuda(velo, aligned)
+    if velo.dim() != 2 or velo.shape[1] != 4 or velo.dtype != torch.float32:
+        raise ValueError("velo must be an [n, 4] float32 tensor (x, y, z, intensity)")
+    velo = velo.contiguous()
+    if aligned is None:
+        aligned = torch.empty_like(velo)
+    check(load().dodt_lidar_to_camera_aligned(_ptr(velo), velo.shape[0], _dbl(trans, 3), _dbl(matrix, 9),
+                                              _ptr(aligned), None, None, 0, 0, None, DODT_F32, 0, None, None, 0,
+                                              _stream()), "dodt_lidar_to_camera_aligned")
+    return aligned
+
+
 # ------------------------------------------------------------------------------------------ anchors
 
 

@@ -232,7 +232,8 @@ int dodt_lidar_to_camera(const float *velo, int64_t n, const double rectified[12
  * rectified / filtered as above. ego_trans[3], ego_matrix[9] (row-major 3x3): host, from the OXTS
  * records (kitti_tracking_utils.py:189-207; dodt_b200.lidar.coordinate_transform); both NULL = no
  * alignment. aligned: optional out, device float32 [n, 4] (moved x, y, z, intensity unchanged),
- * 16-byte aligned, or NULL. */
+ * 16-byte aligned, or NULL. With aligned != NULL and points == NULL only the alignment is done
+ * (point_cloud_transform on its own): rectified, p2, count and workspace are not used then. */
 int dodt_lidar_to_camera_aligned(const float *velo, int64_t n, const double ego_trans[3],
                                  const double ego_matrix[9], float *aligned, const double rectified[12],
                                  const double p2[12], int32_t image_w, int32_t image_h, void *points,
