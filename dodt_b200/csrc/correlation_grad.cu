@@ -31,14 +31,18 @@
 //                             through shared memory, and writes 4 x 8 finished gradients per chunk.
 //                             Every value of the other input is read from HBM once per tile
 //                             (halo re-reads hit L2) instead of (2r+1)^2 times.
-//   corr_grad_flip<R, VEC>    gB as the same contraction: Gf[n,y,x,k'] = G[n, y+2p'-shift,
-//                             x+2o'-shift, D2-1-k'] (shared-memory staged permutation), then
-//                             gB = corr_grad_k1<R, REV=true>(Gf, A): REV walks the displacements
-//                             backwards, which is the reference's summation order for gB, so both
+//   corr_grad_k1<.., FLIP>    gB as the same contraction over the displacement-flipped gradient
+//                             Gf[n,y,x,k'] = G[n, y+2p'-shift, x+2o'-shift, D2-1-k'], walked backwards
+//                             (REV), which is the reference's summation order for gB, so both
 //                             gradients are bit-identical to a scalar restatement that uses fmaf.
+//                             Gf is never materialised (round 1 and 2 wrote it to a workspace with a
+//                             separate pass, corr_grad_flip: 28.5 us and 196 MB of HBM traffic per call):
+//                             a tile gathers its 4 x D2 coefficients per thread from a shared-memory
+//                             copy of the gradient's (8 + 4r) x (64 + 4r) pixel neighbourhood, staged
+//                             eight rows at a time over the two chunk stages.
 //
 // Algorithmic HBM bytes (both gradients, 700x800x32, 25 displacements): read G 56 MB + A, B 2 x 71.68
-// MB, write gA, gB 2 x 71.68 MB = 342.7 MB; the flip pass adds 2 x 70 MB of workspace traffic.
+// MB, write gA, gB 2 x 71.68 MB = 342.7 MB (the neighbourhood rows of gB's gather are re-read from L2).
 #include "common.cuh"
 #include "tma_util.cuh"
 
@@ -141,6 +145,11 @@ struct GradCfg {
   static constexpr int B_FLOATS = BH * BPITCH * kCC;          // one stage
   // the coefficient tile is only needed until it sits in registers: it aliases the two stages
   static constexpr int FLOATS = 2 * B_FLOATS > G_FLOATS ? 2 * B_FLOATS : G_FLOATS;
+  // FLIP (gB straight from the gradient map): the coefficients of a tile come from the BH x BW pixel
+  // neighbourhood of the gradient, staged eight rows at a time (two phases) over the two stages
+  static constexpr int FW = BW * D2;                                    // floats per neighbourhood row
+  static constexpr int F_PITCH = FW + ((2 - FW % 32) + 32) % 32;        // 2 (mod 32) floats
+  static_assert(8 * F_PITCH <= FLOATS, "a flip phase fits the stage memory");
   static constexpr size_t BAR_OFF = ((static_cast<size_t>(FLOATS) * sizeof(float) + 127) / 128) * 128;
   static constexpr size_t SMEM = BAR_OFF + 64;                // + the two full barriers of the TMA feed
 };
@@ -155,7 +164,11 @@ struct GradCfg {
 // TMA: the other input's tiles arrive by cp.async.bulk.tensor (UTMALDG) issued by one thread and
 // completing on an mbarrier, zero fill by the TMA unit (round 2: the forward kernel's feed);
 // otherwise by LDGSTS from every thread (round 1; kept for hosts without tensor maps).
-template <int R, bool REV, int GB, bool TMA>
+// FLIP (with REV): coef is the gradient map itself and the coefficient of tap k = (p, o) of input pixel
+// (y, x) is coef[y + 2p - cshift, x + 2o - cshift, D2-1-k] — what corr_grad_flip used to materialise
+// for the whole map (a 56 MB read + 70 MB write + 70 MB re-read per call) is gathered per tile from a
+// shared-memory copy of the tile's neighbourhood, eight rows per phase.
+template <int R, bool REV, int GB, bool TMA, bool FLIP = false>
 __global__ void __launch_bounds__(kThreads, 2)
 corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, const __grid_constant__ CUtensorMap map_other,
              int batch, int H, int W, int C, int ch, int cw, int cshift, int tiles_x, int tiles_y,
@@ -192,6 +205,54 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, co
     float *dn = dst + static_cast<size_t>(n) * H * W * C;
 
     __syncthreads();   // the previous tile's last chunk has been consumed
+    float gk[kPX][D2];
+    if constexpr (FLIP) {
+      static_assert(REV, "the flipped coefficients belong to the reversed walk");
+      constexpr int kPerRow = Cfg::FW / GE;                         // copies per neighbourhood row
+      constexpr int kIter = (kPerRow + kThreads - 1) / kThreads;
+      const int gx0 = tx0 - Cfg::HALO - cshift;
+      const int f_lo = max(0, -gx0) * D2, f_hi = min(Cfg::BW, cw - gx0) * D2;
+      const int f0 = static_cast<int>(threadIdx.x) * GE;
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll
+        for (int r_ = 0; r_ < 8; ++r_) {
+          const int nr = ph * 8 + r_;
+          if (nr < Cfg::BH) {
+            const int gy = ty0 + nr - Cfg::HALO - cshift;
+            const bool row_ok = gy >= 0 && gy < ch;
+            const long long off = (static_cast<long long>(gy) * cw + gx0) * D2 + f0;
+            const float *src0 = row_ok ? cn + off : cn;             // only dereferenced when ok
+            const uint32_t dst0 = smem_u32(sg + r_ * Cfg::F_PITCH + f0);
+#pragma unroll
+            for (int i = 0; i < kIter; ++i) {
+              const int f = f0 + i * kThreads * GE;
+              if (kPerRow % kThreads == 0 || f < Cfg::FW) {
+                const bool ok = row_ok && f >= f_lo && f < f_hi;
+                cp_async<GB>(dst0 + i * kThreads * GE * 4, ok ? src0 + i * kThreads * GE : cn, ok);
+              }
+            }
+          }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        // tap row pi of pixel row `row` lives in neighbourhood row row + 2 pi
+#pragma unroll
+        for (int pi = 0; pi < WN; ++pi) {
+          const int nr = row + 2 * pi;
+          if ((nr >> 3) == ph) {
+            const float *srow = sg + (nr & 7) * Cfg::F_PITCH;
+#pragma unroll
+            for (int j = 0; j < kPX; ++j)
+#pragma unroll
+              for (int oi = 0; oi < WN; ++oi)
+                gk[j][pi * WN + oi] = srow[(x0 + 2 * j + 2 * oi) * D2 + (D2 - 1 - (pi * WN + oi))];
+          }
+        }
+        __syncthreads();   // the phase has been read: the next one (or the stages) may be filled
+      }
+    } else {
     // ---- coefficients of the tile: each row is a contiguous run of kTW * D2 floats
     // (a row's copies differ by compile-time offsets from one global and one shared base; the
     // columns inside the coefficient map are the float range [f_lo, f_hi) of the row)
@@ -220,12 +281,12 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, co
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    float gk[kPX][D2];
 #pragma unroll
     for (int j = 0; j < kPX; ++j)
 #pragma unroll
       for (int k = 0; k < D2; ++k) gk[j][k] = sg[row * Cfg::G_PITCH + (x0 + 2 * j) * D2 + k];
     __syncthreads();   // sg is dead: the stages may be filled
+    }
 
     // stage the other input's tile with its halo (zero outside the image = padding)
     // Loader thread (ly, lx) copies the 16-byte pieces lx, lx + 16, ... of tile rows ly, ly + 8, ...:
@@ -346,70 +407,9 @@ corr_grad_k1(const float *__restrict__ coef, const float *__restrict__ other, co
   }
 }
 
-// Gf[n,y,x,k'] = G[n, y + 2p' - shift, x + 2o' - shift, D2-1-k'] for input pixel (y,x) in H x W,
-// k' = (p'+R)*WN + (o'+R); zero where the source lies outside the out_h x out_w gradient map.
-// A CTA produces an FT_H x FT_W tile: the source tile with its halo is read in contiguous rows
-// into shared memory, the permuted tile is written in contiguous rows.
-constexpr int kFH = 8, kFW = 32, kFlipThreads = 256;
-// VEC: 16-byte copies in and 16-byte stores out; needs out_w, W, HALO + shift all multiples of 4
-// and 16-byte aligned pointers (then no 16-byte granule straddles the edge of either map).
-template <int R, bool VEC>
-__global__ void __launch_bounds__(kFlipThreads)
-corr_grad_flip(const float *__restrict__ grad, int out_h, int out_w, int H, int W, int shift,
-               float *__restrict__ gf) {
-  constexpr int WN = 2 * R + 1, D2 = WN * WN, HALO = 2 * R;
-  constexpr int SW = kFW + 2 * HALO, SH = kFH + 2 * HALO;
-  constexpr int PITCH = SW * D2 + 4;            // rows stay 16-byte aligned
-  constexpr int GE = VEC ? 4 : 1;
-  extern __shared__ __align__(16) float smem[];
-  const int n = blockIdx.z, ty0 = blockIdx.y * kFH, tx0 = blockIdx.x * kFW;
-  const float *gn = grad + static_cast<size_t>(n) * out_h * out_w * D2;
-  float *fn = gf + static_cast<size_t>(n) * H * W * D2;
-  const int gx0 = tx0 - HALO - shift;
-  // source offset of displacement k' relative to its own pixel: rows 2p', columns 2o', element D2-1-k'
-  __shared__ int lut[D2];
-  if (threadIdx.x < D2) {
-    const int k = threadIdx.x;
-    lut[k] = 2 * (k / WN) * PITCH + 2 * (k % WN) * D2 + (D2 - 1 - k);
-  }
-  // columns inside the gradient map = the float range [f_lo, f_hi) of a staged row
-  const int f_lo = max(0, -gx0) * D2, f_hi = min(SW, out_w - gx0) * D2;
-#pragma unroll 4
-  for (int e = threadIdx.x; e < SH * SW * D2 / GE; e += kFlipThreads) {
-    const int r_ = e / (SW * D2 / GE), f = (e - r_ * (SW * D2 / GE)) * GE;
-    const int gy = ty0 + r_ - HALO - shift;
-    const bool ok = gy >= 0 && gy < out_h && f >= f_lo && f < f_hi;
-    const float *src = ok ? gn + (static_cast<long long>(gy) * out_w + gx0) * D2 + f : gn;
-    cp_async<4 * GE>(smem_u32(smem + r_ * PITCH + f), src, ok);
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-  for (int e = threadIdx.x; e < kFH * kFW * D2 / GE; e += kFlipThreads) {
-    const int r_ = e / (kFW * D2 / GE), f = (e - r_ * (kFW * D2 / GE)) * GE;
-    int px = f / D2, k = f - px * D2;
-    const int y = ty0 + r_;
-    if (y >= H || tx0 + px >= W) continue;
-    float *d = fn + (static_cast<long long>(y) * W + tx0) * D2 + f;
-    int base = r_ * PITCH + px * D2;
-    if constexpr (VEC) {
-      // W % 4 == 0 and tx0 % 4 == 0: the four floats lie in columns < W together
-      float v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[i] = smem[base + lut[k]];
-        if (++k == D2) { k = 0; base += D2; }
-      }
-      *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-      *d = smem[base + lut[k]];
-    }
-  }
-}
-
 template <int R>
 int launch_k1(const float *grad, const float *a, const float *b, const GradGeom &g, float *ga,
-              float *gb, float *ws, cudaStream_t stream) {
+              float *gb, cudaStream_t stream) {
   using Cfg = GradCfg<R>;
   const int shift = g.md - g.pad;
   const int tiles_x = ceil_div(g.W, kTW), tiles_y = ceil_div(g.H, kTH);
@@ -447,19 +447,13 @@ int launch_k1(const float *grad, const float *a, const float *b, const GradGeom 
     if (rc != DODT_OK) return rc;
   }
   if (gb) {
-    constexpr int D2 = Cfg::D2, HALO = Cfg::HALO;
-    const size_t fsmem = (static_cast<size_t>(kFH + 2 * HALO) * ((kFW + 2 * HALO) * D2 + 4)) * sizeof(float);
-    const bool vec = g.out_w % 4 == 0 && g.W % 4 == 0 && (HALO + shift) % 4 == 0 &&
-                     reinterpret_cast<uintptr_t>(grad) % 16 == 0;   // ws is 16-byte aligned
-    auto flip = vec ? corr_grad_flip<R, true> : corr_grad_flip<R, false>;
-    DODT_CUDA_TRY(cudaFuncSetAttribute(flip, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(fsmem)));
-    dim3 fgrid(ceil_div(g.W, kFW), ceil_div(g.H, kFH), g.batch);
-    flip<<<fgrid, kFlipThreads, fsmem, stream>>>(grad, g.out_h, g.out_w, g.H, g.W, shift, ws);
-    DODT_AFTER_LAUNCH();
-    const int rc = wide(ws, g.W, 0)
-                       ? run(corr_grad_k1<R, true, 8, true>, corr_grad_k1<R, true, 8, false>, ws, a, g.H, g.W, 0, gb)
-                       : run(corr_grad_k1<R, true, 4, true>, corr_grad_k1<R, true, 4, false>, ws, a, g.H, g.W, 0, gb);
+    // gB: the same contraction walked backwards over the displacement-flipped gradient, gathered per
+    // tile from the gradient map itself (FLIP)
+    const int rc = wide(grad, g.out_w, shift)
+                       ? run(corr_grad_k1<R, true, 8, true, true>, corr_grad_k1<R, true, 8, false, true>, grad, a,
+                             g.out_h, g.out_w, shift, gb)
+                       : run(corr_grad_k1<R, true, 4, true, true>, corr_grad_k1<R, true, 4, false, true>, grad, a,
+                             g.out_h, g.out_w, shift, gb);
     if (rc != DODT_OK) return rc;
   }
   return DODT_OK;
@@ -497,8 +491,7 @@ size_t dodt_correlation_grad_workspace_bytes(int32_t batch, int32_t height, int3
   if (dodt::fill(batch, height, width, channels, kernel_size, max_displacement, stride_1, stride_2,
                  pad, &g) != DODT_OK)
     return 0;
-  if (!dodt::k1_family(g)) return 0;
-  return static_cast<size_t>(g.batch) * g.H * g.W * g.out_c * sizeof(float);
+  return 0;   // no scratch since the displacement flip is gathered per tile (kept in the ABI)
 }
 
 int dodt_correlation_grad(const float *grad, const float *a, const float *b, int32_t batch,
@@ -514,13 +507,12 @@ int dodt_correlation_grad(const float *grad, const float *a, const float *b, int
   if (rc != DODT_OK) return rc;
   cudaStream_t stream = as_stream(stream_);
   auto al16 = [](const void *p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
-  const size_t need = static_cast<size_t>(g.batch) * g.H * g.W * g.out_c * sizeof(float);
-  if (k1_family(g) && al16(a) && al16(b) && (!grad_a || al16(grad_a)) && (!grad_b || al16(grad_b)) &&
-      (!grad_b || (workspace && workspace_bytes >= need && al16(workspace)))) {
+  (void)workspace;
+  (void)workspace_bytes;
+  if (k1_family(g) && al16(a) && al16(b) && (!grad_a || al16(grad_a)) && (!grad_b || al16(grad_b))) {
     int done = 1;
-    float *ws = static_cast<float *>(workspace);
-    if (g.r == 1) done = launch_k1<1>(grad, a, b, g, grad_a, grad_b, ws, stream);
-    if (g.r == 2) done = launch_k1<2>(grad, a, b, g, grad_a, grad_b, ws, stream);
+    if (g.r == 1) done = launch_k1<1>(grad, a, b, g, grad_a, grad_b, stream);
+    if (g.r == 2) done = launch_k1<2>(grad, a, b, g, grad_a, grad_b, stream);
     if (done <= 0) return done;
   }
   const long long total = static_cast<long long>(g.batch) * g.H * g.W * g.C;

@@ -389,9 +389,9 @@ int dodt_correlation_stream(const float *const *maps, int32_t n_maps, float *con
  * (CorrelateDataBackward0 / CorrelateDataBackward1). Same attributes as the forward op.
  * grad [batch,out_h,out_w,out_c] f32 (the gradient of the forward output), a, b [batch,H,W,C] ->
  * grad_a, grad_b [batch,H,W,C] (either may be NULL: that gradient is skipped).
- * workspace: dodt_correlation_grad_workspace_bytes(...) bytes, 16-byte aligned (0 for parameter
- * sets outside the kernel_size 1 / stride_1 1 / stride_2 2 family, which take the generic kernel;
- * a missing or short workspace also selects the generic kernel for grad_b).
+ * workspace: not used any more (dodt_correlation_grad_workspace_bytes returns 0: the displacement
+ * flip that grad_b needs is gathered per tile inside the kernel); the parameters stay in the ABI and
+ * may be NULL / 0.
  * ---------------------------------------------------------------------------------------- */
 size_t dodt_correlation_grad_workspace_bytes(int32_t batch, int32_t height, int32_t width,
                                              int32_t channels, int32_t kernel_size,

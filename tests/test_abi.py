@@ -85,12 +85,9 @@ def test_host_only_entry_points(lib):
     assert lib.dodt_nms_state_offset(89600) < ops.nms_workspace_bytes(89600)
     assert lib.dodt_compact_workspace_bytes(89600) > 0
     assert lib.dodt_launch_count() >= 0
-    # S4 backward: workspace = the displacement-flipped copy of the gradient, only for the
-    # kernel_size 1 / stride_1 1 / stride_2 2 family; 0 for invalid or generic parameter sets
-    assert ops.correlation_grad_workspace_bytes(1, 700, 800, 32, 1, 5, 1, 2, 5) == 700 * 800 * 25 * 4
-    assert ops.correlation_grad_workspace_bytes(2, 64, 96, 8, 1, 2, 1, 2, 2) == 2 * 64 * 96 * 9 * 4
+    # S4 backward: no scratch since the displacement flip is gathered per tile inside the kernel
+    assert ops.correlation_grad_workspace_bytes(1, 700, 800, 32, 1, 5, 1, 2, 5) == 0
     assert ops.correlation_grad_workspace_bytes(1, 64, 96, 8, 3, 4, 2, 2, 4) == 0
-    assert ops.correlation_grad_workspace_bytes(1, 64, 96, 8, 2, 4, 1, 2, 4) == 0
 
 
 def test_new_entry_points_validate_arguments_on_the_host(lib):
